@@ -1,0 +1,98 @@
+// b2_host.h — internal host-side structures of libb2lz4 (context, workspace).
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/b2lz4.h"
+#include "b2_kernels.h"
+
+namespace b2 {
+
+void set_cuda_error(cudaError_t e, const char* what);
+
+#define B2_CUDA(expr)                                  \
+    do {                                               \
+        cudaError_t _e = (expr);                       \
+        if (_e != cudaSuccess) {                       \
+            ::b2::set_cuda_error(_e, #expr);           \
+            return B2LZ4_ERR_CUDA;                     \
+        }                                              \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = (n + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want + 256);  // +256: 16-byte over-read slack for vector loads
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Small results the device hands back once per call (lives in pinned memory).
+struct HostResults {
+    FrameTotals totals;
+    WalkResult walk;
+    DecodeSummary summary;
+    uint32_t content_sum;
+    uint32_t pad;
+    XxhState xxh;
+};
+
+}  // namespace b2
+
+struct b2lz4_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;   // the context's own stream
+    cudaStream_t side = nullptr;     // content-checksum chain runs here, concurrently
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pointer pipeline
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_t[8] = {};
+    cudaEvent_t ev_pipe[8] = {};
+    std::recursive_mutex mu;
+    bool timing = false;
+    float phase_ms[5] = {0, 0, 0, 0, 0};
+    // workspace
+    b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, hc_work;
+    b2::DevBuf stage_in[2], stage_out[2], stage_aux;
+    b2::PinBuf results, pin_aux;
+    // layout of `small` (device): ticket u32 @0, FrameTotals @64, WalkResult @128, DecodeSummary @192,
+    // content_sum u32 @256, XxhState @320
+    uint32_t* d_ticket() const { return small.as<uint32_t>(); }
+    b2::FrameTotals* d_totals() const { return reinterpret_cast<b2::FrameTotals*>(small.as<uint8_t>() + 64); }
+    b2::WalkResult* d_walk() const { return reinterpret_cast<b2::WalkResult*>(small.as<uint8_t>() + 128); }
+    b2::DecodeSummary* d_summary() const { return reinterpret_cast<b2::DecodeSummary*>(small.as<uint8_t>() + 192); }
+    uint32_t* d_content_sum() const { return reinterpret_cast<uint32_t*>(small.as<uint8_t>() + 256); }
+    b2::XxhState* d_xxh() const { return reinterpret_cast<b2::XxhState*>(small.as<uint8_t>() + 320); }
+    b2::HostResults* h() const { return results.as<b2::HostResults>(); }
+    size_t workspace_bytes() const;
+};
+
+// internal entry points shared between translation units
+int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,
+                         size_t* out, cudaStream_t s, bool body_only);
+int b2_decompress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out, cudaStream_t s);
+int b2_default_ctx(b2lz4_ctx** out);

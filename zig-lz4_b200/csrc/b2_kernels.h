@@ -1,0 +1,88 @@
+// b2_kernels.h — host-visible launchers of the CUDA kernels (internal; the public ABI is include/b2lz4.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "b2_common.cuh"
+
+namespace b2 {
+
+void count_launch();  // bumps the process-wide kernel launch counter (b2lz4_kernel_launch_count)
+
+// K1 — fast compressor (k_compress_fast.cu)
+cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
+                                 uint32_t nblocks, uint32_t max_len, uint32_t accel, uint32_t* ticket, int num_sms,
+                                 cudaStream_t stream);
+
+// K2 — decompressor (k_decompress.cu).  hdr: optional frame block headers (bit31 = stored raw).
+cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint32_t* hdr, uint32_t* out_len,
+                              int32_t* status, uint32_t nblocks, const uint8_t* dict, uint32_t dict_len,
+                              uint32_t* ticket, int num_sms, cudaStream_t stream);
+// size-only parse (no output written): natural decoded size of each block, for foreign frames whose
+// non-final blocks are not exactly blockSize
+cudaError_t launch_decoded_size(const BlockSet& in, const uint32_t* hdr, uint32_t* out_len, int32_t* status,
+                                uint32_t nblocks, int num_sms, cudaStream_t stream);
+
+// K3 — HC hash-chain compressor (k_compress_hc.cu).  work: per-resident-warp tables (hc_work_bytes()).
+size_t hc_work_bytes(int num_sms);
+cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
+                               uint32_t nblocks, int nb_searches, uint8_t* work, uint32_t* ticket, int num_sms,
+                               cudaStream_t stream);
+
+// K4 — XXH32 (k_xxh32.cu)
+// per-block checksum of the *stored* bytes: slot data if csize < raw len, else the raw block
+cudaError_t launch_xxh32_stored(const BlockSet& slots, const BlockSet& raw, const uint32_t* csize, uint32_t* sums,
+                                uint32_t nblocks, cudaStream_t stream);
+// per-block checksum of explicit (off,len) ranges — frame decode verification
+cudaError_t launch_xxh32_ranges(const uint8_t* base, const uint64_t* off, const uint32_t* hdr, uint32_t* sums,
+                                uint32_t nblocks, cudaStream_t stream);
+// serial running XXH32 over one buffer; state is 12 u32: v[4], tail[4 words], tail_len, seed, total lo/hi
+struct XxhState {
+    uint32_t v[4];
+    uint32_t tail[4];
+    uint32_t tail_len;
+    uint32_t seed;
+    uint32_t total_lo, total_hi;
+};
+cudaError_t launch_xxh32_init(XxhState* st, uint32_t seed, cudaStream_t stream);
+cudaError_t launch_xxh32_update(XxhState* st, const uint8_t* p, uint64_t n, cudaStream_t stream);
+cudaError_t launch_xxh32_final(const XxhState* st, uint32_t* out, cudaStream_t stream);
+
+// K5/K6/K7 — frame scan, assembly, index walk (k_frame.cu)
+struct FrameTotals {       // written by the device, read back once per call
+    uint64_t body_bytes;   // sum of block records
+    uint32_t first_bad;    // first block with status != 0 (0xFFFFFFFF if none)
+    int32_t bad_status;
+};
+cudaError_t launch_scan_records(const uint32_t* csize, const int32_t* status, uint32_t nblocks, uint64_t stride,
+                                uint64_t total, uint32_t block_checksum, uint64_t* rec_off, FrameTotals* totals,
+                                cudaStream_t stream);
+cudaError_t launch_assemble(const BlockSet& slots, const BlockSet& raw, const uint32_t* csize, const uint32_t* sums,
+                            const uint64_t* rec_off, uint8_t* body, uint32_t nblocks, uint32_t block_checksum,
+                            int num_sms, cudaStream_t stream);
+// writes end mark (+ content checksum from *content_sum if non-null) after the body
+cudaError_t launch_finalize(uint8_t* frame, uint64_t header_size, const FrameTotals* totals,
+                            const uint32_t* content_sum, cudaStream_t stream);
+
+struct WalkResult {
+    uint32_t nblocks;      // blocks found (may exceed capacity: then only the first `capacity` were stored)
+    uint32_t terminal;     // 0 = end mark seen, 1 = ran off the end without end mark, 2 = truncated (FrameSizeWrong)
+    uint64_t end_pos;      // srcPos after the walk (position of the content checksum if any)
+    uint32_t max_stored;   // largest stored block size
+    uint32_t pad;
+};
+cudaError_t launch_walk(const uint8_t* frame, uint64_t n, uint64_t start, uint32_t block_checksum, uint64_t* off,
+                        uint32_t* hdr, uint32_t capacity, WalkResult* res, cudaStream_t stream);
+
+struct DecodeSummary {
+    uint32_t first_bad;        // first block index with a checksum / decode problem (0xFFFFFFFF none)
+    int32_t bad_kind;          // 1 = block checksum mismatch, 2 = decode error, 3 = raw block no room
+    int32_t bad_status;        // the lz4 status of the failing decode
+    uint32_t layout_ok;        // 1 if every non-final block decoded to exactly block_size
+    uint64_t total;            // decoded bytes (valid when no error and layout_ok)
+};
+cudaError_t launch_decode_summary(const uint32_t* out_len, const int32_t* status, const uint32_t* sums_calc,
+                                  const uint8_t* frame, const uint64_t* off, const uint32_t* hdr, uint32_t nblocks,
+                                  uint32_t block_size, uint32_t block_checksum, DecodeSummary* out,
+                                  cudaStream_t stream);
+
+}  // namespace b2

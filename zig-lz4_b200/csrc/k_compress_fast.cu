@@ -1,0 +1,226 @@
+// k_compress_fast.cu — K1: LZ4 fast block compressor, many independent blocks, one warp per block.
+//
+// Semantics: byte-identical to the reference's greedy single-probe matcher,
+//   lz4.compressFast / compressDefault, /root/reference/src/lz4.zig:292-447
+//   (+ compressAsLiterals :449-482, finishCompression :484-519).
+//
+// How a sequential hash-table algorithm is made warp-parallel without changing a single output byte:
+// the search loop of the reference visits a *predictable* sequence of positions from a search start q
+// (iteration k: ip_k, step s_k — src/lz4.zig:329-333) and stops at the first position whose table
+// candidate is a valid match.  A warp evaluates 32 consecutive iterations at once:
+//   * every lane computes its iteration's (ip_k, s_k) in closed form, applies the early-exit test
+//     `forwardIp > mflimitPlusOne` (:335) *before* probing, hashes its 4 bytes and reads the table;
+//   * intra-window ordering is restored with __match_any_sync on the hash: a lane's candidate is the
+//     position of the nearest earlier lane with the same hash, else the table value (that is exactly
+//     what the table would hold after the earlier lanes' put()s — :350);
+//   * __ballot_sync finds the first lane with a valid match (:345-348); only lanes up to and
+//     including it commit their put()s, later-lane-wins per bucket;
+//   * the 63 repeated probes of ip0+1 that the reference's step schedule performs (step == 0 while
+//     searchMatchNb < 64) are provable no-ops on table and output and are skipped; their
+//     exit tests are implied by the next distinct iteration's test.
+// Match extension (:401-413) compares 4 bytes per lane per round and finds the end with ballot/ffs.
+// Literal runs are copied with 16-byte aligned stores (b2::warp_copy).
+//
+// Memory: input is read straight from global memory through the read-only path (L1/L2 — a 64 KiB
+// block's window stays cache-resident while its warp works on it); the 4096-entry hash table lives in
+// shared memory: u16 entries when every block is <= 64 KiB (8 KiB/warp), u32 otherwise (16 KiB/warp).
+// Blocks are handed to warps through a global ticket so long and short blocks balance.
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+
+namespace b2 {
+
+constexpr int K1_WARPS = 4;
+constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int HASH_ENTRIES = 4096;  // LZ4_HASH_SIZE_U32, src/lz4.zig:33
+
+__device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * HASH_MULTIPLIER) >> 20; }  // :75-77
+
+// F(x) = sum_{u<x} (u >> 6): cumulative step of the reference's `step = searchMatchNb >> 6` schedule.
+__device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
+    uint32_t A = x >> 6, B = x & 63;
+    return 32u * A * (A - 1u) + B * A;
+}
+
+// 255-run length extension bytes (src/lz4.zig:368-382 / :416-429)
+__device__ __forceinline__ void write_len_ext(uint8_t* p, uint32_t L, uint32_t cnt, uint32_t lane) {
+    for (uint32_t i = lane; i < cnt; i += 32) p[i] = (i + 1 == cnt) ? (uint8_t)((L - 15u) % 255u) : (uint8_t)255;
+}
+
+template <typename TableT>
+__device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
+                               TableT* table, uint32_t accel, uint32_t lane, uint32_t& olen, int& st) {
+    st = ST_OK;
+    olen = 0;
+    if (n == 0) return;                                          // :299
+    if (n > LZ4_MAX_INPUT_SIZE) { st = ST_INPUT_TOO_LARGE; return; }  // :296
+    uint32_t op = 0, anchor = 0;
+
+    if (n >= MFLIMIT + 1) {                                      // :302
+        {   // HashTable.init(), :307
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4* t4 = reinterpret_cast<uint4*>(table);
+            constexpr uint32_t NV = HASH_ENTRIES * sizeof(TableT) / 16;
+#pragma unroll 4
+            for (uint32_t i = lane; i < NV; i += 32) t4[i] = z;
+            __syncwarp();
+        }
+        const uint32_t lim = n - MFLIMIT;         // mflimitPlusOne, :313
+        const uint32_t mlimit = n - LASTLITERALS;  // matchLimit, :314
+        const uint32_t a0 = accel < 1 ? 1u : (accel > ACCELERATION_MAX ? ACCELERATION_MAX : accel);  // :321
+        const uint32_t skip = a0 < 64 ? 64 - a0 : 0;  // repeated (step == 0) iterations that are no-ops
+        const uint32_t F0 = step_prefix(a0);
+        const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+        uint32_t q = 1;                                          // :317
+
+        while (q < lim) {                                        // :320
+            // ---------------- search: windows of 32 iterations of the loop at :329-355 ----------------
+            uint32_t j0 = 0, mpos = 0, mcand = 0;
+            bool found = false;
+            for (;;) {
+                uint32_t j = j0 + lane;
+                uint32_t k = j + 1 + (j >= 2 ? skip : 0);        // reference iteration number (1-based)
+                uint32_t p, s;
+                if (k == 1) { p = q; s = a0; }
+                else { uint32_t x = a0 + k - 2; s = x >> 6; p = q + a0 + (step_prefix(x) - F0); }
+                bool can = (p + s <= lim);                       // !(forwardIp > mflimitPlusOne), :335
+                uint32_t em = __ballot_sync(FULL, !can);
+                uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;  // first iteration that exits
+                bool active = lane < E;
+                uint32_t v = 0, h = 0x80000000u | lane, cand = 0;
+                if (active) { v = ldg_u32(src + p); h = hash4(v); cand = table[h]; }
+                uint32_t peers = __match_any_sync(FULL, h);
+                uint32_t prev = peers & lt;
+                int sl = prev ? 31 - __clz(prev) : (int)lane;
+                uint32_t pp = __shfl_sync(FULL, p, sl);
+                if (prev) cand = pp;                             // what an earlier iteration just put()
+                bool valid = active && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;  // :345-347
+                if (valid) valid = (ldg_u32(src + cand) == v);   // :348
+                uint32_t vm = __ballot_sync(FULL, valid);
+                uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
+                uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
+                bool commit = active && lane <= L && ((peers & gt & le) == 0);  // put(), :350
+                __syncwarp();
+                if (commit) table[h] = (TableT)p;
+                __syncwarp();
+                if (vm) { mpos = __shfl_sync(FULL, p, L); mcand = __shfl_sync(FULL, cand, L); found = true; break; }
+                if (E < 32) break;                               // -> finishCompression, :335-338
+                j0 += 32;
+            }
+            if (!found) break;
+
+            // ---------------- match extension, :401-413 ----------------
+            uint32_t ip = mpos;
+            const uint32_t LL = ip - anchor;                     // :360
+            const uint32_t offset = ip - mcand;                  // :395
+            uint32_t a = ip + MINMATCH, b = mcand + MINMATCH, ml = 0;
+            for (;;) {
+                uint32_t al = a + 4 * lane;
+                uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+                uint32_t cnt = 0;
+                if (nb) {
+                    uint32_t x = ldg_u32(src + al) ^ ldg_u32(src + b + 4 * lane);
+                    uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                    cnt = mm < nb ? mm : nb;
+                }
+                uint32_t stopm = __ballot_sync(FULL, cnt < 4);
+                if (stopm) {
+                    uint32_t f = (uint32_t)__ffs(stopm) - 1;
+                    ml += 4 * f + __shfl_sync(FULL, cnt, f);
+                    break;
+                }
+                ml += 128; a += 128; b += 128;
+            }
+            ip += MINMATCH + ml;
+
+            // ---------------- emit sequence, :362-432 ----------------
+            const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+            const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+            const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+            if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // monotone in op: see DESIGN.md
+            uint8_t* o = dst + op;
+            if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
+            write_len_ext(o + 1, LL, nll, lane);
+            warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+            uint8_t* o2 = o + 1 + nll + LL;
+            if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
+            write_len_ext(o2 + 2, ml, nml, lane);
+            op = seq_end;
+            anchor = ip;                                         // :435
+            if (ip < lim) {                                      // :438-442
+                if (lane == 0) table[hash4(ldg_u32(src + ip))] = (TableT)ip;
+                ip += 1;
+            }
+            __syncwarp();
+            q = ip;
+        }
+    }
+
+    // ---------------- last literals: compressAsLiterals :449-482 / finishCompression :484-519 ----------------
+    const uint32_t LL = n - anchor;
+    const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+    const uint32_t total = op + 1 + nll + LL;
+    if (total > cap) { st = ST_OUTPUT_TOO_SMALL; return; }
+    uint8_t* o = dst + op;
+    if (lane == 0) o[0] = (uint8_t)((LL < 15 ? LL : 15u) << 4);
+    write_len_ext(o + 1, LL, nll, lane);
+    warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+    olen = total;
+}
+
+template <typename TableT>
+__global__ void __launch_bounds__(K1_THREADS) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
+                                                              int32_t* __restrict__ status, uint32_t nblocks,
+                                                              uint32_t accel, uint32_t* ticket) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    TableT* table = reinterpret_cast<TableT*>(smem_raw) + (threadIdx.x >> 5) * HASH_ENTRIES;
+    const uint32_t lane = lane_id();
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(ticket, 1u);
+        blk = __shfl_sync(FULL, blk, 0);
+        if (blk >= nblocks) break;
+        const uint8_t* src; uint32_t n;
+        uint8_t* dst; uint32_t cap;
+        in.get(blk, src, n);
+        out.get(blk, dst, cap);
+        uint32_t olen; int st;
+        compress_block<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
+        if (lane == 0) {
+            out_len[blk] = st == ST_OK ? olen : 0u;
+            status[blk] = st;
+        }
+        __syncwarp();
+    }
+}
+
+// Host launcher.  max_len decides the table entry width.
+cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
+                                 uint32_t nblocks, uint32_t max_len, uint32_t accel, uint32_t* ticket, int num_sms,
+                                 cudaStream_t stream) {
+    if (nblocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    const bool small = max_len <= 65536;
+    const size_t smem = (size_t)K1_WARPS * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_compress_fast<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             K1_WARPS * HASH_ENTRIES * (int)sizeof(uint32_t));
+        cudaFuncSetAttribute(k_compress_fast<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             K1_WARPS * HASH_ENTRIES * (int)sizeof(uint16_t));
+        attr_done = true;
+    }
+    const int ctas_per_sm = small ? 7 : 3;  // 227 KiB / (32 | 64) KiB
+    uint32_t want = (nblocks + K1_WARPS - 1) / K1_WARPS;
+    uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
+    uint32_t grid = want < maxg ? want : maxg;
+    if (small)
+        k_compress_fast<uint16_t><<<grid, K1_THREADS, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+    else
+        k_compress_fast<uint32_t><<<grid, K1_THREADS, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b2

@@ -1,0 +1,292 @@
+// k_compress_hc.cu — K3: LZ4HC hash-chain compressor (levels 3..9), many independent blocks, one warp
+// per block.
+//
+// Semantics: byte-identical to the reference's greedy hash-chain path
+//   compressHashChain  /root/reference/src/lz4hc.zig:976-1064
+//   insertHC :491-510, insertAndGetWiderMatch :538-681 (iLowLimit == ip, longest == 3, no chainSwap),
+//   encodeSequence :308-386 (limitedOutput), pattern analysis :626-678 with the F8 guard of the oracle
+//   (matchIndex == 0 => no pattern candidate; the reference underflows a u32 there).
+//
+// Warp-parallel restatement of a sequential algorithm:
+//   * insertHC for a run of positions is done 32 positions per step: every lane hashes its position,
+//     reads the bucket, and __match_any_sync restores the sequential order inside the step (a lane's
+//     predecessor is the nearest earlier lane with the same hash, else the bucket value); the last lane
+//     of each hash group writes the bucket.
+//   * the chain walk is serial by nature (m -= chain[m]); the warp walks up to 32 hops, parks hop a's
+//     candidate in lane a, then all lanes measure their candidate's match length at once.  The
+//     reference's order-dependent rules are recovered with ballots: a candidate replaces the best only
+//     if strictly longer (first lane holding the maximum wins), and the early exit `len > nbSearches`
+//     (:613) cuts the chunk at the first such lane, which also defines the final matchIndex that the
+//     pattern analysis reads.
+//   * countPattern / reverseCountPattern / the final length of the chosen match are warp-wide
+//     compares (128 bytes per round).
+// State: hashTable u32[32768] + chainTable u16[65536] per resident warp, in global memory (L2
+// resident).  The reference zero-fills 256 KiB per call (:1450); here bucket values carry a per-warp
+// epoch base (value = base + index; anything below the base reads as 0 = empty), so nothing is
+// re-zeroed between blocks, and the chain table never needs zeroing (only inserted slots are read).
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+
+namespace b2 {
+
+constexpr int HC_WARPS = 4;                 // warps per CTA
+constexpr int HC_CTAS_PER_SM = 2;
+constexpr uint32_t HC_HASH = 32768, HC_CHAIN = 65536;
+
+struct HcWork {
+    uint32_t hash[HC_HASH];
+    uint16_t chain[HC_CHAIN];
+    uint32_t base;          // epoch base of the bucket values (persists across launches)
+    uint32_t pad[15];
+};
+
+size_t hc_work_bytes(int num_sms) { return (size_t)num_sms * HC_CTAS_PER_SM * HC_WARPS * sizeof(HcWork); }
+
+__device__ __forceinline__ uint32_t hashHC(uint32_t v) { return (v * HASH_MULTIPLIER) >> 17; }  // :129-131
+
+__device__ __forceinline__ void write_len_ext_hc(uint8_t* p, uint32_t L, uint32_t cnt, uint32_t lane) {
+    for (uint32_t i = lane; i < cnt; i += 32) p[i] = (i + 1 == cnt) ? (uint8_t)((L - 15u) % 255u) : (uint8_t)255;
+}
+
+// number of bytes equal to `b` in src[from, limit) counted forward from `from` (countPattern :170-199
+// for a one-byte-repeat pattern)
+__device__ uint32_t warp_count_byte_fwd(const uint8_t* __restrict__ src, uint32_t from, uint32_t limit, uint32_t pat32,
+                                        uint32_t lane) {
+    uint32_t total = 0;
+    for (;;) {
+        uint32_t a = from + 4 * lane;
+        uint32_t nb = a >= limit ? 0u : (limit - a >= 4 ? 4u : limit - a);
+        uint32_t cnt = 0;
+        if (nb) {
+            uint32_t x = ldg_u32(src + a) ^ pat32;
+            uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+            cnt = mm < nb ? mm : nb;
+        }
+        uint32_t stopm = __ballot_sync(FULL, cnt < 4);
+        if (stopm) {
+            uint32_t f = (uint32_t)__ffs(stopm) - 1;
+            return total + 4 * f + __shfl_sync(FULL, cnt, f);
+        }
+        total += 128; from += 128;
+    }
+}
+
+// number of bytes equal to `b` immediately before `from`, not going below position 0
+// (reverseCountPattern :202-222 with iLow = block start)
+__device__ uint32_t warp_count_byte_bwd(const uint8_t* __restrict__ src, uint32_t from, uint32_t b, uint32_t lane) {
+    uint32_t total = 0;
+    for (;;) {
+        // lane l looks at byte from-1-l
+        bool inr = from > lane;
+        bool eq = inr && (uint32_t)__ldg(src + (from - 1 - lane)) == b;
+        uint32_t stopm = __ballot_sync(FULL, !eq);
+        if (stopm) return total + ((uint32_t)__ffs(stopm) - 1);
+        total += 32; from -= 32;
+    }
+}
+
+// common prefix of src[a..] and src[m..], a limited to < limit (lz4Count :234-264), one lane
+__device__ __forceinline__ uint32_t lane_count(const uint8_t* __restrict__ src, uint32_t a, uint32_t m, uint32_t limit) {
+    uint32_t c = 0;
+    while (a + 4 <= limit) {
+        uint32_t x = ldg_u32(src + a) ^ ldg_u32(src + m);
+        if (x) return c + ((uint32_t)(__ffs(x) - 1) >> 3);
+        a += 4; m += 4; c += 4;
+    }
+    while (a < limit && __ldg(src + a) == __ldg(src + m)) { a++; m++; c++; }
+    return c;
+}
+
+__device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
+                                  HcWork* w, int nbs, uint32_t lane, uint32_t& olen, int& st) {
+    st = ST_OK;
+    olen = 0;
+    if (n == 0) return;                                                  // :1443
+    if (n > LZ4_MAX_INPUT_SIZE) { st = ST_INPUT_TOO_LARGE; return; }     // :1442
+    if (cap == 0) { st = ST_OUTPUT_TOO_SMALL; return; }                  // :1461
+    uint32_t op = 0, anchor = 0;
+    if (n < MFLIMIT + 1) {                                               // :995 encodeLiterals :1394-1425
+        if (cap < n + 1 + n / 255) { st = ST_OUTPUT_TOO_SMALL; return; }
+        if (lane == 0) dst[0] = (uint8_t)(n << 4);
+        warp_copy<true>(dst + 1, src, n, lane);
+        olen = n + 1;
+        return;
+    }
+    // epoch base for this block's bucket values
+    uint32_t base = w->base;
+    if (base > 0xFFFFFFFFu - n - 16u) {   // would wrap: re-zero once
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* t4 = reinterpret_cast<uint4*>(w->hash);
+        for (uint32_t i = lane; i < HC_HASH * 4 / 16; i += 32) t4[i] = z;
+        base = 0;
+    }
+    __syncwarp();
+    if (lane == 0) w->base = base + n;
+    uint32_t* H = w->hash;
+    uint16_t* C = w->chain;
+    const bool patternAnalysis = nbs > 128;                              // :983
+    const uint32_t mflimit = n - MFLIMIT, mlimit = n - LASTLITERALS;
+    const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+    uint32_t ip = 0, ntu = 0;
+
+    while (ip <= mflimit) {                                              // :1009
+        // ---------------- insertHC(ctx, ip): positions [ntu, ip), :491-510 ----------------
+        while (ntu < ip) {
+            uint32_t idx = ntu + lane;
+            bool act = idx < ip;
+            uint32_t h = 0x80000000u | lane, prev = 0;
+            if (act) {
+                h = hashHC(ldg_u32(src + idx));
+                uint32_t v = H[h];
+                prev = v >= base ? v - base : 0;
+            }
+            uint32_t peers = __match_any_sync(FULL, h);
+            uint32_t pm = peers & lt;
+            if (pm) prev = idx - (lane - (31 - __clz(pm)));
+            uint32_t delta = idx - prev;
+            if (delta > MAX_DISTANCE) delta = MAX_DISTANCE;
+            __syncwarp();
+            if (act) {
+                C[idx & (HC_CHAIN - 1)] = (uint16_t)delta;
+                if ((peers & gt) == 0) H[h] = base + idx;
+            }
+            __syncwarp();
+            ntu += 32;
+        }
+        ntu = ip;
+
+        // ---------------- insertAndGetWiderMatch, :538-681 ----------------
+        const uint32_t pattern = ldg_u32(src + ip);
+        uint32_t best_len = MINMATCH - 1, best_off = 0;
+        uint32_t m;
+        { uint32_t v = H[hashHC(pattern)]; m = v >= base ? v - base : 0; }   // :563
+        if (m != 0) {                                                        // :566
+            int attempts = nbs;
+            uint32_t final_m = m;
+            bool done = false;
+            while (!done) {
+                uint32_t my_cand = 0, cnt = 0;
+                for (uint32_t a = 0; a < 32; a++) {
+                    if (!(m > 0 && attempts > 0)) { done = true; final_m = m; break; }           // :571
+                    if (m > ip || ip - m > MAX_DISTANCE) { done = true; final_m = m; break; }    // :573
+                    attempts--;
+                    if (lane == a) my_cand = m;
+                    cnt = a + 1;
+                    uint32_t delta = C[m & (HC_CHAIN - 1)];                                      // :619
+                    if (delta == 0 || delta > m) { done = true; final_m = m; break; }
+                    m -= delta;
+                }
+                uint32_t len = 0;
+                if (lane < cnt && ldg_u32(src + my_cand) == pattern)                             // :586
+                    len = MINMATCH + lane_count(src, ip + MINMATCH, my_cand + MINMATCH, mlimit);
+                uint32_t xm = __ballot_sync(FULL, len > (uint32_t)nbs);                          // :613
+                uint32_t X = xm ? (uint32_t)__ffs(xm) - 1 : 32;
+                uint32_t l = (lane < cnt && lane <= X) ? len : 0;
+                uint32_t mx = __reduce_max_sync(FULL, l);
+                if (mx > best_len) {                                                             // :607
+                    uint32_t who = (uint32_t)__ffs(__ballot_sync(FULL, l == mx)) - 1;
+                    best_len = mx;
+                    best_off = ip - __shfl_sync(FULL, my_cand, who);
+                }
+                if (xm) { done = true; final_m = __shfl_sync(FULL, my_cand, X); }
+            }
+            if (patternAnalysis) {                                                               // :626
+                uint32_t delta = C[final_m & (HC_CHAIN - 1)];
+                if (delta == 1 && ((pattern & 0xFFFF) == (pattern >> 16)) && ((pattern & 0xFF) == (pattern >> 24))) {
+                    uint32_t srcPat = warp_count_byte_fwd(src, ip + 4, mlimit, pattern, lane) + 4;  // :633
+                    if (final_m != 0) {                                                          // F8 guard
+                        uint32_t cand = final_m - 1;                                             // :636
+                        uint32_t lowest = ip < 65536 ? 0 : ip - MAX_DISTANCE;                    // :553-554
+                        if (cand >= lowest && ldg_u32(src + cand) == pattern) {                  // :637,:644
+                            uint32_t fwd = warp_count_byte_fwd(src, cand + 4, mlimit, pattern, lane) + 4;
+                            uint32_t back = warp_count_byte_bwd(src, cand, pattern & 0xFF, lane);
+                            uint32_t a = cand - back;
+                            uint32_t limq = a > lowest ? a : lowest;
+                            uint32_t limitedBack = cand - limq;                                  // :653
+                            uint32_t seg = limitedBack + fwd;
+                            uint32_t maxML = seg < srcPat ? seg : srcPat;
+                            uint32_t newIdx = (seg >= srcPat && fwd <= srcPat) ? cand + fwd - srcPat : cand - limitedBack;
+                            if (maxML > best_len && ip - newIdx <= MAX_DISTANCE) {               // :669
+                                best_len = maxML;
+                                best_off = ip - newIdx;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (best_len < MINMATCH || best_off == 0) { ip += 1; continue; }                         // :1013
+
+        // ---------------- encodeSequence (limitedOutput), :308-386 ----------------
+        const uint32_t LL = ip - anchor;
+        if ((uint64_t)op + LL / 255 + LL + 8 > cap) { st = ST_OUTPUT_TOO_SMALL; return; }        // :320-325
+        const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+        const uint32_t mlc = best_len - MINMATCH;
+        const uint32_t nml = mlc >= ML_MASK ? (mlc - ML_MASK) / 255 + 1 : 0;
+        uint8_t* o = dst + op;
+        uint8_t* o2 = o + 1 + nll + LL;
+        if ((uint64_t)(op + 1 + nll + LL + 2) + mlc / 255 + 6 > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // :355-359
+        if (lane == 0) {
+            o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (mlc < 15 ? mlc : 15u));
+            o2[0] = (uint8_t)(best_off & 0xFF);
+            o2[1] = (uint8_t)(best_off >> 8);
+        }
+        write_len_ext_hc(o + 1, LL, nll, lane);
+        warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+        write_len_ext_hc(o2 + 2, mlc, nml, lane);
+        op += 1 + nll + LL + 2 + nml;
+        ip += best_len;                                                                          // :382
+        anchor = ip;
+    }
+
+    // ---------------- last literals, :1035-1061 ----------------
+    const uint32_t LL = n - anchor;
+    if (LL > 0) {
+        const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+        if ((uint64_t)op + 1 + nll + LL > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // :1037 (+ no-overflow, as the oracle)
+        uint8_t* o = dst + op;
+        if (lane == 0) o[0] = (uint8_t)((LL < 15 ? LL : 15u) << 4);
+        write_len_ext_hc(o + 1, LL, nll, lane);
+        warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+        op += 1 + nll + LL;
+    }
+    olen = op;
+}
+
+__global__ void __launch_bounds__(HC_WARPS * 32) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
+                                                               int32_t* __restrict__ status, uint32_t nblocks, int nbs,
+                                                               HcWork* work, uint32_t* ticket) {
+    const uint32_t lane = lane_id();
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    HcWork* w = work + gw;
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(ticket, 1u);
+        blk = __shfl_sync(FULL, blk, 0);
+        if (blk >= nblocks) break;
+        const uint8_t* src; uint32_t n;
+        uint8_t* dst; uint32_t cap;
+        in.get(blk, src, n);
+        out.get(blk, dst, cap);
+        uint32_t olen; int st;
+        compress_block_hc(src, n, dst, cap, w, nbs, lane, olen, st);
+        if (lane == 0) { out_len[blk] = st == ST_OK ? olen : 0u; status[blk] = st; }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status, uint32_t nblocks,
+                               int nb_searches, uint8_t* work, uint32_t* ticket, int num_sms, cudaStream_t stream) {
+    if (nblocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    uint32_t maxg = (uint32_t)(num_sms * HC_CTAS_PER_SM);
+    uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
+    uint32_t grid = want < maxg ? want : maxg;
+    k_compress_hc<<<grid, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
+                                                      reinterpret_cast<HcWork*>(work), ticket);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b2

@@ -1,0 +1,250 @@
+// k_xxh32.cu — K4: XXH32 (seed-parameterised) on the device.
+//
+// The reference hashes through Zig's std.hash.XxHash32 (standard XXH32): block checksums over the
+// *stored* bytes of each block (src/lz4f.zig:422-427, verified at :590-600) and one running content
+// checksum over all raw bytes (:375,:384-386,:437-441 / :560,:617-619,:625-635).
+//
+// XXH32 is four dependent lane recurrences acc = rotl(acc + x*P2, 13) * P1 — a serial chain that
+// cannot be split or prefix-scanned.  So:
+//   * block checksums: ONE THREAD PER BLOCK, all four accumulators in one thread (4-way ILP), 16-byte
+//     vector loads with several stripes in flight.  Parallelism comes from the number of blocks.
+//   * content checksum: one warp; 32 lanes stream 2 KiB tiles into shared memory (double buffered),
+//     lanes 0..3 each run one accumulator chain.  ~14 cycles per 16-byte stripe, inherently.
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+
+namespace b2 {
+
+constexpr uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t xround(uint32_t acc, uint32_t x) { return rotl32(acc + x * P2, 13) * P1; }
+
+__device__ __forceinline__ uint32_t xxh_finish(uint32_t h, const uint8_t* p, uint32_t n) {
+    // tail of < 16 bytes: 4-byte words then single bytes, then avalanche
+    while (n >= 4) {
+        h = rotl32(h + ldg_u32(p) * P3, 17) * P4;
+        p += 4; n -= 4;
+    }
+    while (n) {
+        h = rotl32(h + (uint32_t)__ldg(p) * P5, 11) * P1;
+        p += 1; n -= 1;
+    }
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    return h;
+}
+
+// Whole-buffer XXH32 by a single thread.
+__device__ uint32_t xxh32_thread(const uint8_t* __restrict__ p, uint32_t len, uint32_t seed) {
+    uint32_t h;
+    const uint8_t* q = p;
+    uint32_t rem = len;
+    if (len >= 16) {
+        uint32_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4* q4 = reinterpret_cast<const uint4*>(p);
+            uint32_t nst = len >> 4, i = 0;
+            for (; i + 4 <= nst; i += 4) {
+                uint4 a = __ldg(q4 + i), b = __ldg(q4 + i + 1), c = __ldg(q4 + i + 2), d = __ldg(q4 + i + 3);
+                v1 = xround(v1, a.x); v2 = xround(v2, a.y); v3 = xround(v3, a.z); v4 = xround(v4, a.w);
+                v1 = xround(v1, b.x); v2 = xround(v2, b.y); v3 = xround(v3, b.z); v4 = xround(v4, b.w);
+                v1 = xround(v1, c.x); v2 = xround(v2, c.y); v3 = xround(v3, c.z); v4 = xround(v4, c.w);
+                v1 = xround(v1, d.x); v2 = xround(v2, d.y); v3 = xround(v3, d.z); v4 = xround(v4, d.w);
+            }
+            for (; i < nst; i++) {
+                uint4 a = __ldg(q4 + i);
+                v1 = xround(v1, a.x); v2 = xround(v2, a.y); v3 = xround(v3, a.z); v4 = xround(v4, a.w);
+            }
+            q = p + ((size_t)nst << 4);
+            rem = len & 15;
+        } else {
+            // unaligned payload (frame decode): realign word by word
+            uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+            const uint32_t sh = (uint32_t)(a & 3) * 8;
+            uint32_t nst = len >> 4;
+            uint32_t w0 = __ldg(w);
+            for (uint32_t i = 0; i < nst; i++) {
+                uint32_t w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+                // the 5th word is only dereferenced when it holds valid bytes
+                uint32_t w4 = (sh || i + 1 < nst || (len & 15)) ? __ldg(w + 4) : 0u;
+                v1 = xround(v1, __funnelshift_r(w0, w1, sh));
+                v2 = xround(v2, __funnelshift_r(w1, w2, sh));
+                v3 = xround(v3, __funnelshift_r(w2, w3, sh));
+                v4 = xround(v4, __funnelshift_r(w3, w4, sh));
+                w0 = w4;
+                w += 4;
+            }
+            q = p + ((size_t)nst << 4);
+            rem = len & 15;
+        }
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+    } else {
+        h = seed + P5;
+    }
+    h += len;
+    return xxh_finish(h, q, rem);
+}
+
+__global__ void k_xxh32_stored(BlockSet slots, BlockSet raw, const uint32_t* __restrict__ csize, uint32_t* __restrict__ sums,
+                               uint32_t nblocks) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    const uint8_t* rp; uint32_t rn;
+    raw.get(i, rp, rn);
+    uint32_t c = csize[i];
+    const uint8_t* p = rp; uint32_t n = rn;
+    if (c < rn) { const uint8_t* sp; uint32_t sn; slots.get(i, sp, sn); p = sp; n = c; }  // src/lz4f.zig:407-408
+    sums[i] = xxh32_thread(p, n, 0);
+}
+
+__global__ void k_xxh32_ranges(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off,
+                               const uint32_t* __restrict__ hdr, uint32_t* __restrict__ sums, uint32_t nblocks) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    sums[i] = xxh32_thread(base + off[i], hdr[i] & 0x7FFFFFFFu, 0);
+}
+
+cudaError_t launch_xxh32_stored(const BlockSet& slots, const BlockSet& raw, const uint32_t* csize, uint32_t* sums,
+                                uint32_t nblocks, cudaStream_t stream) {
+    if (nblocks == 0) return cudaSuccess;
+    // 32 threads per CTA spreads the (few, long) per-thread chains over all SMs
+    const int threads = 32;
+    k_xxh32_stored<<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(slots, raw, csize, sums, nblocks);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xxh32_ranges(const uint8_t* base, const uint64_t* off, const uint32_t* hdr, uint32_t* sums,
+                                uint32_t nblocks, cudaStream_t stream) {
+    if (nblocks == 0) return cudaSuccess;
+    const int threads = 32;
+    k_xxh32_ranges<<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(base, off, hdr, sums, nblocks);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ running (content) checksum ----
+__global__ void k_xxh32_init(XxhState* st, uint32_t seed) {
+    st->v[0] = seed + P1 + P2; st->v[1] = seed + P2; st->v[2] = seed; st->v[3] = seed - P1;
+    st->tail[0] = st->tail[1] = st->tail[2] = st->tail[3] = 0;
+    st->tail_len = 0; st->seed = seed; st->total_lo = 0; st->total_hi = 0;
+}
+
+constexpr uint32_t TILE = 2048;  // bytes per shared-memory tile (128 stripes)
+
+// One warp.  Consumes n bytes at p, continuing from *st (src/lz4f.zig:385 XxHash32.update).
+__global__ void __launch_bounds__(32) k_xxh32_update(XxhState* st, const uint8_t* __restrict__ p, uint64_t n) {
+    __shared__ __align__(16) uint32_t tile[2][TILE / 4];
+    __shared__ uint8_t tailb[32];
+    const uint32_t lane = threadIdx.x;
+    uint32_t acc = lane < 4 ? st->v[lane] : 0;
+    uint32_t tail_len = st->tail_len;
+    uint64_t total = ((uint64_t)st->total_hi << 32) | st->total_lo;
+    if (lane < 16) tailb[lane] = (uint8_t)(st->tail[lane >> 2] >> ((lane & 3) * 8));
+    __syncwarp();
+    total += n;
+    // 1) top up a pending partial stripe
+    if (tail_len) {
+        uint32_t take = 16 - tail_len;
+        if ((uint64_t)take > n) take = (uint32_t)n;
+        if (lane < take) tailb[tail_len + lane] = __ldg(p + lane);
+        __syncwarp();
+        tail_len += take; p += take; n -= take;
+        if (tail_len == 16) {
+            if (lane < 4) {
+                uint32_t x = (uint32_t)tailb[4 * lane] | ((uint32_t)tailb[4 * lane + 1] << 8) |
+                             ((uint32_t)tailb[4 * lane + 2] << 16) | ((uint32_t)tailb[4 * lane + 3] << 24);
+                acc = xround(acc, x);
+            }
+            tail_len = 0;
+        }
+        __syncwarp();
+    }
+    // 2) full stripes, tile by tile
+    uint64_t nst = n >> 4;                          // stripes remaining
+    const uint32_t bo = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+    const uint4* s16 = reinterpret_cast<const uint4*>(p - bo);
+    uint64_t done = 0;                               // stripes consumed
+    uint4 r[4];
+    auto load_tile = [&](uint64_t first) {          // stripes [first, first+128) -> registers
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint64_t sidx = first + lane + 32u * u;
+            if (sidx < nst) {
+                if (bo == 0) r[u] = __ldg(s16 + sidx);
+                else r[u] = extract16(__ldg(s16 + sidx), __ldg(s16 + sidx + 1), bo);
+            }
+        }
+    };
+    int buf = 0;
+    if (nst) load_tile(0);
+    while (done < nst) {
+        uint32_t cnt = (uint32_t)(nst - done < 128 ? nst - done : 128);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t s = lane + 32u * u;
+            if (s < cnt) reinterpret_cast<uint4*>(tile[buf])[s] = r[u];
+        }
+        __syncwarp();
+        if (done + 128 < nst) load_tile(done + 128);  // prefetch the next tile while the chains run
+        if (lane < 4) {
+            const uint32_t* t = tile[buf] + lane;
+#pragma unroll 8
+            for (uint32_t s = 0; s < cnt; s++) acc = xround(acc, t[4 * s]);
+        }
+        done += cnt;
+        buf ^= 1;
+    }
+    __syncwarp();
+    // 3) stash the new tail
+    uint32_t rem = (uint32_t)(n & 15);
+    const uint8_t* tp = p + (nst << 4);
+    if (lane < rem) tailb[tail_len + lane] = __ldg(tp + lane);
+    tail_len += rem;
+    __syncwarp();
+    if (lane < 4) {
+        st->v[lane] = acc;
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) {
+            uint32_t idx = 4 * lane + b;
+            if (idx < tail_len) w |= (uint32_t)tailb[idx] << (8 * b);
+        }
+        st->tail[lane] = w;
+    }
+    if (lane == 0) { st->tail_len = tail_len; st->total_lo = (uint32_t)total; st->total_hi = (uint32_t)(total >> 32); }
+}
+
+__global__ void k_xxh32_final(const XxhState* st, uint32_t* out) {
+    uint64_t total = ((uint64_t)st->total_hi << 32) | st->total_lo;
+    uint32_t h;
+    if (total >= 16) h = rotl32(st->v[0], 1) + rotl32(st->v[1], 7) + rotl32(st->v[2], 12) + rotl32(st->v[3], 18);
+    else h = st->seed + P5;
+    h += (uint32_t)total;
+    uint32_t n = st->tail_len;
+    uint32_t i = 0;
+    while (n >= 4) { h = rotl32(h + st->tail[i] * P3, 17) * P4; i++; n -= 4; }
+    uint32_t w = i < 4 ? st->tail[i] : 0;
+    while (n) { h = rotl32(h + (w & 0xFF) * P5, 11) * P1; w >>= 8; n--; }
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    *out = h;
+}
+
+cudaError_t launch_xxh32_init(XxhState* st, uint32_t seed, cudaStream_t stream) {
+    k_xxh32_init<<<1, 1, 0, stream>>>(st, seed);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_xxh32_update(XxhState* st, const uint8_t* p, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_xxh32_update<<<1, 32, 0, stream>>>(st, p, n);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_xxh32_final(const XxhState* st, uint32_t* out, cudaStream_t stream) {
+    k_xxh32_final<<<1, 1, 0, stream>>>(st, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b2
