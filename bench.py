@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (BASELINE.json configs[1]).
+
+Workload: 1 GiB of synthetic mixed-entropy data per GPU (four classes rotating
+every 64 KiB), one lz4f frame with 64 KiB independent blocks, default fast mode.  One step = compress the
+buffer into a frame and decompress that frame back.  `value` = uncompressed bytes / (t_compress +
+t_decompress) with everything resident in HBM, CUDA-event timed on the launching stream, max over ranks.
+`e2e` = the same round trip through the host-pointer C-ABI (pinned host buffers, H2D + D2H inside the
+timed region).  N > 1: the frame shards by block range, one rank per GPU (weak scaling: 1 GiB per rank);
+the only exchange is an all-gather of the per-rank body sizes (the offset computation of SURVEY §8e).
+
+--impl reference times the CPU oracle (C restatement of the Zig reference; no zig toolchain exists in
+this image) on all host threads for the same metric/config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "LZ4 compress & decompress GB/s (uncompressed)"
+GIB = 1 << 30
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bytes", type=int, default=GIB, help="uncompressed bytes per GPU (default 1 GiB)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_prefs_pair(n):
+    import zig_lz4_b200 as z
+    zp = z.lz4f.Preferences(blockSizeID=z.lz4f.BlockSizeID.max64KB, blockMode=z.lz4f.BlockMode.independent)
+    return zp
+
+
+def cpu_arm(nbytes, threads, steps, warmup):
+    """The CPU oracle (port of the Zig reference) on `threads` host threads: compress + decompress."""
+    import numpy as np
+    import b2oracle as o
+    from zig_lz4_b200 import datagen
+    data = datagen.generate(nbytes, mode=datagen.MIXED, span=65536)
+    p = o.make_prefs(block_size_id=4, block_mode=1)
+    import ctypes as C
+    L = o.lib()
+    cap = o.compress_frame_bound(nbytes, p)
+    dst = np.empty(cap, dtype=np.uint8)
+    back = np.empty(nbytes, dtype=np.uint8)
+    out = C.c_size_t(0)
+    tc = td = 0.0
+    csize = 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rc = L.b2o_compress_frame_mt(data.ctypes.data, nbytes, dst.ctypes.data, cap, C.byref(p), C.byref(out), threads)
+        t1 = time.perf_counter()
+        assert rc == 0
+        csize = out.value
+        rc = L.b2o_decompress_frame_mt(dst.ctypes.data, csize, back.ctypes.data, nbytes, C.byref(out), threads)
+        t2 = time.perf_counter()
+        assert rc == 0 and out.value == nbytes
+        if it >= warmup:
+            tc += t1 - t0
+            td += t2 - t1
+    assert (back == data).all()
+    return {"compress_gbs": nbytes * steps / tc / 1e9, "decompress_gbs": nbytes * steps / td / 1e9,
+            "roundtrip_gbs": nbytes * steps / (tc + td) / 1e9, "ratio": nbytes / csize, "ms_per_step": (tc + td) / steps * 1e3}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import b2oracle as o
+    threads = o.hardware_threads()
+    sample = min(args.bytes, GIB)
+    r = cpu_arm(sample, threads, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["roundtrip_gbs"], 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic mixed-entropy, 64 KiB independent blocks, default fast mode, "
+                               "compress+decompress", "bytes": sample, "block_size": 65536},
+        "compress_gbs": round(r["compress_gbs"], 4), "decompress_gbs": round(r["decompress_gbs"], 4), "ratio": round(r["ratio"], 4),
+        "cpu_baseline": {"value": round(r["roundtrip_gbs"], 4), "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": "%d MiB of the same workload per step; C restatement of the Zig reference "
+                                   "(oracle/), one block per task on all host threads" % (sample >> 20)},
+        "e2e": {"value": round(r["roundtrip_gbs"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zig_lz4_b200 as z
+    from zig_lz4_b200 import datagen
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.bytes
+    bs = 65536
+    zp = make_prefs_pair(n)
+    ctx = z.Context(local)
+
+    # ---- synthetic shard of this rank (rank r holds blocks [r*B, (r+1)*B) of the world-sized frame) ----
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    datagen.fill_ptr(host.data_ptr(), n, seed=0x4C5A3442 + rank * (n // 65536), mode=datagen.MIXED, span=65536)
+    src = host.to(dev, non_blocking=False)
+    cap = z.lz4f.compressFrameBound(n, zp)
+    comp = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
+    back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    s = stream.cuda_stream
+    sizes_dev = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        """compress the shard, exchange body sizes (N>1), decompress it back.  Returns (csize, tc_ms, td_ms)."""
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if world == 1:
+            csize = ctx.compress_frame_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, s)
+        else:
+            csize = ctx.compress_blocks_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, s)
+            mine = torch.tensor([csize], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(sizes_dev, mine)          # per-GPU compressed-size offsets
+        ph_c = ctx.last_phase_ms()
+        e1.record(stream)
+        if world == 1:
+            m = ctx.decompress_frame_dev(comp.data_ptr(), csize, back.data_ptr(), n, s)
+        else:
+            m = ctx.decompress_blocks_dev(comp.data_ptr(), csize, back.data_ptr(), n, bs, False, s)
+        ph_d = ctx.last_phase_ms()
+        e2.record(stream)
+        e2.synchronize()
+        assert m == n
+        return csize, e0.elapsed_time(e1), e1.elapsed_time(e2), ph_c, ph_d
+
+    ctx.set_timing(True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    assert torch.equal(back[:n], src), "round trip mismatch"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = z.kernel_launch_count()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record(stream)
+    tc = td = 0.0
+    kc = kd = walk = 0.0
+    csize = 0
+    for _ in range(args.steps):
+        csize, a, b, ph_c, ph_d = step()
+        tc += a; td += b
+        kc += ph_c[0]; kd += ph_d[0]; walk += ph_d[2]
+    t_all1.record(stream)
+    barrier()
+    launches = z.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_all0.elapsed_time(t_all1)
+    if world > 1:
+        t = torch.tensor([total_ms, tc, td], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, tc, td = [float(x) for x in t.tolist()]
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+    comp_gbs = world * n / (tc / args.steps * 1e-3) / 1e9
+    dec_gbs = world * n / (td / args.steps * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (K1, the compressor) and of the decompressor (K2) ----
+    peak, peak_src = peaks()
+    kc_ms = kc / args.steps
+    kd_ms = kd / args.steps
+    roof_c = (n + csize) / (kc_ms * 1e-3) / 1e9
+    roof_d = (n + csize) / (kd_ms * 1e-3) / 1e9
+
+    # ---- e2e: host-pointer C-ABI, pinned host buffers, H2D and D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hcomp = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        hback = torch.empty(n, dtype=torch.uint8).pin_memory()
+        hsrc = np.frombuffer((C_ubyte_array(host.data_ptr(), n)), dtype=np.uint8)
+        hdst = np.frombuffer((C_ubyte_array(hcomp.data_ptr(), cap)), dtype=np.uint8)
+        hbk = np.frombuffer((C_ubyte_array(hback.data_ptr(), n)), dtype=np.uint8)
+        zpf = zp
+
+        def e2e_step():
+            cs = ctx.compress_frame(hsrc, zpf, dst=hdst)
+            m = ctx.decompress_frame(hdst[:cs], dst=hbk)
+            assert m == n
+            return cs
+
+        for _ in range(2):
+            cs = e2e_step()
+        assert (hbk == hsrc).all()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cs = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(world * n * args.steps / dt / 1e9, 4), "unit": "GB/s", "h2d_bytes_per_step": world * (n + cs),
+               "d2h_bytes_per_step": world * (cs + n), "ms_per_step": round(dt / args.steps * 1e3, 3),
+               "api": "b2lz4f_compress_frame_ctx + b2lz4f_decompress_frame_ctx (host pointers, pinned)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d MiB/GPU synthetic mixed-entropy (text/binary/redundant/random rotating every "
+                                   "64 KiB), one lz4f frame, 64 KiB independent blocks, default fast mode, compress + "
+                                   "decompress" % (n >> 20),
+                       "bytes_per_gpu": n, "block_size": bs, "sharding": "block range per rank, all-gather of body sizes",
+                       "l2": "inputs (1 GiB raw, ~0.5 GiB compressed) are larger than the 126 MB L2; no flush needed"},
+            "compress_gbs": round(comp_gbs, 3), "decompress_gbs": round(dec_gbs, 3), "ratio": round(n / csize, 4),
+            "roofline": {"bound": "hbm", "kernel": "k_compress_fast", "achieved": round(roof_c, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(roof_c / peak, 5), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": n + csize, "kernel_ms": round(kc_ms, 4)},
+            "roofline_decompress": {"bound": "hbm", "kernel": "k_decompress", "achieved": round(roof_d, 2), "peak": peak,
+                                    "unit": "GB/s", "frac": round(roof_d / peak, 5), "traffic": None,
+                                    "algorithmic_bytes": n + csize, "kernel_ms": round(kd_ms, 4),
+                                    "index_walk_ms": round(walk / args.steps, 4)},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import b2oracle as o
+            threads = o.hardware_threads()
+            sample = min(n, GIB)
+            r = cpu_arm(sample, threads, 1, 1)
+            line["cpu_baseline"] = {"value": round(r["roundtrip_gbs"], 4), "unit": "GB/s", "cores": threads, "kind": "port",
+                                    "compress_gbs": round(r["compress_gbs"], 4), "decompress_gbs": round(r["decompress_gbs"], 4),
+                                    "sample": "%d MiB of the same workload, 1 warm-up + 1 timed pass; C restatement of the Zig "
+                                              "reference (oracle/), one block per task on all host threads" % (sample >> 20)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_ubyte_array(ptr, n):
+    import ctypes as C
+    return (C.c_uint8 * n).from_address(ptr)
+
+
+if __name__ == "__main__":
+    main()
