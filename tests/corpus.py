@@ -3,6 +3,8 @@ classes.  Each entry cites the reference test it comes from."""
 import random
 import struct
 
+import numpy as np
+
 
 def xoshiro256pp_bytes(seed, n):
     """Zig std.Random.DefaultPrng (Xoshiro256++ seeded through SplitMix64) `bytes()` as best restated
@@ -97,3 +99,49 @@ def f8_hazard_input():
     b[70000:70005] = b"XXXXX"
     b[65533:65542] = b"Y" * 9
     return bytes(b)
+
+
+def synth_lz4_stream(rng, nseq, ll_max=20, ml_max=20, near=64, p_near=0.5, p_long=0.02, tail=5):
+    """A hand-assembled valid LZ4 block with `nseq` sequences and a literal tail: random literal-run and
+    match lengths, offsets biased to the last `near` bytes (dense dependencies between neighbouring
+    sequences, overlapping matches with offset < length) and a few long runs.  Returns (stream, decoded)."""
+    out = bytearray()
+    s = bytearray()
+
+    def put_len(v):
+        while v >= 255:
+            s.append(255); v -= 255
+        s.append(v)
+
+    for _ in range(nseq):
+        ll = int(rng.integers(0, ll_max + 1))
+        ml = int(rng.integers(4, ml_max + 1))
+        if rng.random() < p_long:
+            ll = int(rng.integers(15, 700))
+        if rng.random() < p_long:
+            ml = int(rng.integers(19, 3000))
+        if not out and ll == 0:
+            ll = 1
+        lits = rng.integers(0, 256, size=ll, dtype=np.uint8).tobytes()
+        pos = len(out) + ll
+        if rng.random() < p_near:
+            off = int(rng.integers(1, min(near, pos) + 1))
+        else:
+            off = int(rng.integers(1, min(65535, pos) + 1))
+        s.append((min(ll, 15) << 4) | min(ml - 4, 15))
+        if ll >= 15:
+            put_len(ll - 15)
+        s += lits
+        s += bytes([off & 255, off >> 8])
+        if ml - 4 >= 15:
+            put_len(ml - 4 - 15)
+        out += lits
+        for i in range(ml):
+            out.append(out[pos - off + i])
+    lits = rng.integers(0, 256, size=tail, dtype=np.uint8).tobytes()
+    s.append(min(tail, 15) << 4)
+    if tail >= 15:
+        put_len(tail - 15)
+    s += lits
+    out += lits
+    return bytes(s), bytes(out)

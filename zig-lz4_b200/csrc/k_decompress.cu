@@ -5,8 +5,20 @@
 // and order of checks, its leniency (no last-5-literals / MFLIMIT end rules) and its two quirks
 // (src.len == 0 -> 0, dst.len == 0 -> 0 without error, :97-98).
 //
-// The token chain is parsed by the whole warp in lock-step (every lane holds ip/op); the byte work is
-// spread over the lanes:
+// Two tiers share one block:
+//   FAST tier (decode_block_fast): the token chain is the only serial part of LZ4 decoding, so the warp
+//   walks it for up to 32 sequences at a time touching nothing but the token bytes (one uniform byte
+//   load + ~8 integer ops per sequence), hands sequence k to lane k, and then all 32 sequences are
+//   expanded at once: a warp scan of (LL + ML) gives every lane its output position, each lane copies
+//   its own literal run, and the match copies are resolved in dependency rounds (a lane may copy once
+//   no pending match of an earlier lane overlaps its source range; the first pending lane always may,
+//   so the rounds terminate; a lane's own forward overlap, offset < length, is safe because one thread
+//   copies in ascending order).  Sequences that are long (> LONG_SEQ bytes) are copied cooperatively by
+//   the whole warp with 16-byte vector accesses.  Anything irregular — a stream end within 18 bytes,
+//   offset 0, a match reaching before dst (dictionary or corruption), output overflow — is not
+//   decided here: the fast tier stops at the start of that batch and the exact tier takes over.
+//   EXACT tier (decode_block): lock-step parse with the reference's checks in the reference's order;
+//   the byte work is spread over the lanes:
 //   * 255-run length extensions are scanned 32 bytes at a time with a ballot,
 //   * literals are copied with 16-byte aligned stores (b2::warp_copy, read-only source path),
 //   * a match copy with offset >= length is a plain vector copy; an overlapping match (offset <
@@ -17,6 +29,7 @@
 //     continue at dst[0..].
 #include "b2_common.cuh"
 #include "b2_kernels.h"
+#include <cstdlib>
 
 namespace b2 {
 
@@ -65,12 +78,11 @@ __device__ __forceinline__ void match_copy(uint8_t* d, const uint8_t* s, uint32_
 template <bool WRITE>
 __device__ void decode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
                              const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
-                             uint32_t& olen, int& st) {
+                             uint32_t ip, uint32_t op, uint32_t& olen, int& st) {
     st = ST_OK;
     olen = 0;
     if (n == 0) return;    // :97
     if (cap == 0) return;  // :98
-    uint32_t ip = 0, op = 0;
     const uint32_t iend = n, oend = cap;
     for (;;) {
         if (ip >= iend) break;                                          // :113
@@ -128,7 +140,153 @@ __device__ void decode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_
     olen = op;
 }
 
-__global__ void __launch_bounds__(K2_THREADS) k_decompress(BlockSet in, OutSet out, const uint32_t* __restrict__ hdr,
+
+// ------------------------------------------------------------------------------------------------
+// FAST tier.  Sequences whose copies exceed LONG_SEQ bytes are copied by the whole warp.
+constexpr uint32_t LONG_SEQ = 24;
+// A plain token (LL < 15, ML nibble < 15) at position t touches bytes up to t + 1 + 14 + 2.
+constexpr uint32_t PLAIN_SPAN = 18;
+// Length fields above this are left to the exact tier (keeps the 32-bit prefix sums exact).
+constexpr uint32_t FAST_LEN_MAX = 1u << 24;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= (uint32_t)d) v += t;
+    }
+    return v;
+}
+
+// Number of lanes whose (non-decreasing across lanes) value is <= x, capped at 31.
+__device__ __forceinline__ uint32_t count_le(uint32_t sorted_v, uint32_t x) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        uint32_t v = __shfl_sync(FULL, sorted_v, c + step - 1);
+        if (v <= x) c += step;
+    }
+    return c;
+}
+
+__device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                  const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                  uint32_t& olen, int& st) {
+    uint32_t ip = 0, op = 0;
+    if (n > PLAIN_SPAN && cap > 0) {
+        const uint32_t iend = n;
+        const uint32_t isafe = n - PLAIN_SPAN;  // plain tokens below this read in bounds without checks
+        for (;;) {
+            // ---------------- serial part: walk up to 32 tokens, sequence k goes to lane k ----------------
+            const uint32_t ip0 = ip;
+            uint32_t myLit = 0, myLL = 0, myML = 0;
+            uint32_t k = 0;
+            bool stop = false;  // the exact tier must take over after this batch
+            if (lane < 4 && ip0 + 1024 + lane * 128 < iend) prefetch_l2(src + ip0 + 1024 + lane * 128);
+#pragma unroll 4
+            for (; k < 32; k++) {
+                if (ip >= isafe) { stop = true; break; }
+                const uint32_t t = __ldg(src + ip);
+                uint32_t LL = t >> 4, ML = t & ML_MASK;
+                if (LL == RUN_MASK || ML == ML_MASK) {
+                    // extended lengths: bounds-checked walk (src/lz4.zig:120-131, :157-168)
+                    uint32_t p = ip + 1;
+                    if (LL == RUN_MASK && !read_len_ext(src, p, iend, LL, lane)) { stop = true; break; }
+                    const uint32_t lit = p;
+                    if (LL > FAST_LEN_MAX || (uint64_t)p + LL + 2 > iend) { stop = true; break; }
+                    p += LL + 2;
+                    if (ML == ML_MASK && !read_len_ext(src, p, iend, ML, lane)) { stop = true; break; }
+                    if (ML > FAST_LEN_MAX) { stop = true; break; }
+                    if (lane == k) { myLit = lit; myLL = LL; myML = ML + MINMATCH; }
+                    ip = p;
+                } else {
+                    if (lane == k) { myLit = ip + 1; myLL = LL; myML = ML + MINMATCH; }
+                    ip += LL + 3;
+                }
+            }
+            if (k == 0) break;
+            // ---------------- parallel part ----------------
+            const bool valid = lane < k;
+            uint32_t off = 1;
+            if (valid) off = (uint32_t)__ldg(src + myLit + myLL) | ((uint32_t)__ldg(src + myLit + myLL + 1) << 8);
+            const uint32_t len = myLL + myML;  // 0 on idle lanes
+            const uint32_t incl = warp_incl_scan(len, lane);
+            const uint32_t o0 = op + incl - len;         // where this sequence's literals go
+            const uint32_t ms = o0 + myLL;               // where its match goes
+            const uint32_t batch_len = __shfl_sync(FULL, incl, 31);
+            // offset 0 (:154), match before dst (:181/:231), output overflow (:137/:174): exact tier decides
+            const bool odd = valid && (off == 0 || off > ms);
+            if (__ballot_sync(FULL, odd) != 0 || batch_len > cap - op) { ip = ip0; break; }
+
+            // literals: every lane copies its own short run, long runs go warp-wide
+            {
+                const bool lng = myLL > LONG_SEQ;
+                const uint32_t nl = lng ? 0u : myLL;
+                const uint32_t mx = __reduce_max_sync(FULL, nl);
+                const uint8_t* ls = src + myLit;
+                uint8_t* ld = dst + o0;
+#pragma unroll 4
+                for (uint32_t i = 0; i < mx; i++)
+                    if (i < nl) ld[i] = __ldg(ls + i);
+                uint32_t lm = __ballot_sync(FULL, lng);
+                while (lm) {
+                    const int j = __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    warp_copy<true>(dst + __shfl_sync(FULL, o0, j), src + __shfl_sync(FULL, myLit, j),
+                                    __shfl_sync(FULL, myLL, j), lane);
+                }
+            }
+            __syncwarp();
+
+            // matches: dependency rounds
+            {
+                const uint32_t s = ms - off;                           // source start
+                const uint32_t e = (off < myML) ? ms : s + myML;       // source end outside its own output
+                const uint32_t mend = valid ? ms + myML : 0xFFFFFFFFu; // non-decreasing across lanes
+                const uint32_t mstart = valid ? ms : 0xFFFFFFFFu;
+                uint32_t dep = 0;
+                if (__ballot_sync(FULL, valid && e > op) != 0) {
+                    // lanes [lo, hi) hold the matches that overlap [s, e): mend_j > s and ms_j < e
+                    const uint32_t lo = count_le(mend, s);
+                    const uint32_t hi = count_le(mstart, e - 1);
+                    dep = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+                }
+                const bool lng = myML > LONG_SEQ;
+                bool pending = valid;
+                uint32_t pm = __ballot_sync(FULL, pending);
+                while (pm) {
+                    const bool go = pending && (pm & dep) == 0;
+                    const uint32_t nm = (go && !lng) ? myML : 0u;
+                    const uint32_t mx = __reduce_max_sync(FULL, nm);
+                    uint8_t* md = dst + ms;
+                    const uint8_t* msrc = dst + s;
+#pragma unroll 4
+                    for (uint32_t i = 0; i < mx; i++)
+                        if (i < nm) md[i] = msrc[i];
+                    uint32_t gm = __ballot_sync(FULL, go && lng);
+                    while (gm) {
+                        const int j = __ffs(gm) - 1;
+                        gm &= gm - 1;
+                        const uint32_t jms = __shfl_sync(FULL, ms, j), joff = __shfl_sync(FULL, off, j);
+                        match_copy(dst + jms, dst + jms - joff, joff, __shfl_sync(FULL, myML, j), lane);
+                    }
+                    if (go) pending = false;
+                    __syncwarp();
+                    pm = __ballot_sync(FULL, pending);
+                }
+            }
+            op += batch_len;
+            if (stop) break;
+        }
+    }
+    // the exact tier finishes the block (or decides the error) from a state where all earlier sequences are complete
+    decode_block<true>(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, olen, st);
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in, OutSet out, const uint32_t* __restrict__ hdr,
                                                            uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
                                                            uint32_t nblocks, const uint8_t* __restrict__ dict,
                                                            uint32_t dict_len, int has_dict, uint32_t* ticket) {
@@ -148,7 +306,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_decompress(BlockSet in, OutSet o
             if (n > cap) st = ST_RAW_NO_ROOM;
             else { warp_copy<true>(dst, src, n, lane); olen = n; }
         } else {
-            decode_block<true>(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, olen, st);
+            decode_block_fast(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, olen, st);
         }
         if (lane == 0) {
             out_len[blk] = st == ST_OK ? olen : 0u;
@@ -170,7 +328,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_decoded_size(BlockSet in, const 
         in.get(blk, src, n);
         uint32_t olen = 0; int st = ST_OK;
         if (hdr && (hdr[blk] & 0x80000000u)) olen = n;
-        else decode_block<false>(src, n, nullptr, 0xFFFFFFFFu, nullptr, 0, false, lane, olen, st);
+        else decode_block<false>(src, n, nullptr, 0xFFFFFFFFu, nullptr, 0, false, lane, 0, 0, olen, st);
         if (lane == 0) { out_len[blk] = olen; status[blk] = st; }
     }
 }
@@ -182,10 +340,17 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
-    uint32_t maxg = (uint32_t)(num_sms * 16);  // 16 CTAs x 4 warps = 64 warps / SM
+    // occupancy variant: 8 CTAs x 4 warps (<= 64 registers, no spills) or 10 (<= 48 registers); B2_K2_OCC picks
+    static int occ = 0;
+    if (!occ) { const char* e = getenv("B2_K2_OCC"); occ = (e && atoi(e) == 10) ? 10 : 8; }
+    uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
-    k_decompress<<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len,
-                                                  dict != nullptr ? 1 : 0, ticket);
+    if (occ == 10)
+        k_decompress<10><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len,
+                                                          dict != nullptr ? 1 : 0, ticket);
+    else
+        k_decompress<8><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len,
+                                                         dict != nullptr ? 1 : 0, ticket);
     count_launch();
     return cudaGetLastError();
 }
