@@ -36,6 +36,22 @@ constexpr int HASH_ENTRIES = 4096;  // LZ4_HASH_SIZE_U32, src/lz4.zig:33
 
 __device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * HASH_MULTIPLIER) >> 20; }  // :75-77
 
+// Unaligned little-endian u32 from the (read-only) input: always two aligned words + funnel shift.  The
+// second word holds a valid input byte whenever p + 4 <= n - 1, which every caller guarantees
+// (search positions are <= n - 12, extension reads stop before n - 5).
+__device__ __forceinline__ uint32_t ld_u32x(const uint8_t* __restrict__ p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Pulls the 32-byte sector that holds *p into L1 (result unused; nothing ever waits on it).
+__device__ __forceinline__ void touch_sector(const uint8_t* p) {
+    uint32_t d;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d) : "l"(p));
+}
+
 // F(x) = sum_{u<x} (u >> 6): cumulative step of the reference's `step = searchMatchNb >> 6` schedule.
 __device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
     uint32_t A = x >> 6, B = x & 63;
@@ -74,6 +90,11 @@ __device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint
         uint32_t q = 1;                                          // :317
 
         while (q < lim) {                                        // :320
+            // the forward window is read through L1: keep the next lines coming
+            if (lane == 0) {
+                if (q + 384 < n) prefetch_l1(src + q + 384);
+                if (q + 4096 < n) prefetch_l2(src + q + 4096);
+            }
             // ---------------- search: windows of 32 iterations of the loop at :329-355 ----------------
             uint32_t j0 = 0, mpos = 0, mcand = 0;
             bool found = false;
@@ -88,14 +109,19 @@ __device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint
                 uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;  // first iteration that exits
                 bool active = lane < E;
                 uint32_t v = 0, h = 0x80000000u | lane, cand = 0;
-                if (active) { v = ldg_u32(src + p); h = hash4(v); cand = table[h]; }
+                if (active) { v = ld_u32x(src + p); h = hash4(v); cand = table[h]; }
                 uint32_t peers = __match_any_sync(FULL, h);
                 uint32_t prev = peers & lt;
                 int sl = prev ? 31 - __clz(prev) : (int)lane;
                 uint32_t pp = __shfl_sync(FULL, p, sl);
                 if (prev) cand = pp;                             // what an earlier iteration just put()
                 bool valid = active && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;  // :345-347
-                if (valid) valid = (ldg_u32(src + cand) == v);   // :348
+                if (valid) {
+                    const uint8_t* cp = src + cand;
+                    // the extension reads [cand + 4, cand + 20) next: bring its second sector along
+                    if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && cand + 19 < n) touch_sector(cp + 19);
+                    valid = (ld_u32x(cp) == v);                  // :348
+                }
                 uint32_t vm = __ballot_sync(FULL, valid);
                 uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
                 uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
@@ -114,41 +140,73 @@ __device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint
             const uint32_t LL = ip - anchor;                     // :360
             const uint32_t offset = ip - mcand;                  // :395
             uint32_t a = ip + MINMATCH, b = mcand + MINMATCH, ml = 0;
-            for (;;) {
-                uint32_t al = a + 4 * lane;
-                uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
-                uint32_t cnt = 0;
-                if (nb) {
-                    uint32_t x = ldg_u32(src + al) ^ ldg_u32(src + b + 4 * lane);
-                    uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                    cnt = mm < nb ? mm : nb;
+            {   // first 16 bytes on four lanes (their sectors are in L1 by now); most matches end here
+                uint32_t cnt = 4;
+                if (lane < 4) {
+                    const uint32_t al = a + 4 * lane;
+                    const uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+                    cnt = 0;
+                    if (nb) {
+                        const uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+                        const uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                        cnt = mm < nb ? mm : nb;
+                    }
                 }
-                uint32_t stopm = __ballot_sync(FULL, cnt < 4);
+                const uint32_t stopm = __ballot_sync(FULL, cnt < 4);
                 if (stopm) {
-                    uint32_t f = (uint32_t)__ffs(stopm) - 1;
-                    ml += 4 * f + __shfl_sync(FULL, cnt, f);
-                    break;
+                    const uint32_t f = (uint32_t)__ffs(stopm) - 1;
+                    ml = 4 * f + __shfl_sync(FULL, cnt, f);
+                } else {
+                    ml = 16; a += 16; b += 16;
+                    for (;;) {
+                        uint32_t al = a + 4 * lane;
+                        uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+                        uint32_t c2 = 0;
+                        if (nb) {
+                            uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+                            uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                            c2 = mm < nb ? mm : nb;
+                        }
+                        uint32_t sm = __ballot_sync(FULL, c2 < 4);
+                        if (sm) {
+                            uint32_t f = (uint32_t)__ffs(sm) - 1;
+                            ml += 4 * f + __shfl_sync(FULL, c2, f);
+                            break;
+                        }
+                        ml += 128; a += 128; b += 128;
+                    }
                 }
-                ml += 128; a += 128; b += 128;
             }
             ip += MINMATCH + ml;
 
             // ---------------- emit sequence, :362-432 ----------------
-            const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
-            const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
-            const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
-            if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // monotone in op: see DESIGN.md
-            uint8_t* o = dst + op;
-            if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
-            write_len_ext(o + 1, LL, nll, lane);
-            warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
-            uint8_t* o2 = o + 1 + nll + LL;
-            if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
-            write_len_ext(o2 + 2, ml, nml, lane);
-            op = seq_end;
+            if (LL < RUN_MASK && ml < ML_MASK) {
+                // short form (no length extension bytes): token | literals | offset = LL + 3 <= 17 bytes, one byte per lane
+                const uint32_t seq_end = op + LL + 3;
+                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // monotone in op: see DESIGN.md
+                uint32_t bv = (LL << 4) | ml;
+                if (lane >= 1 && lane <= LL) bv = __ldg(src + anchor + lane - 1);
+                else if (lane == LL + 1) bv = offset;
+                else if (lane == LL + 2) bv = offset >> 8;
+                if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
+                op = seq_end;
+            } else {
+                const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+                const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+                const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }
+                uint8_t* o = dst + op;
+                if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
+                write_len_ext(o + 1, LL, nll, lane);
+                warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+                uint8_t* o2 = o + 1 + nll + LL;
+                if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
+                write_len_ext(o2 + 2, ml, nml, lane);
+                op = seq_end;
+            }
             anchor = ip;                                         // :435
             if (ip < lim) {                                      // :438-442
-                if (lane == 0) table[hash4(ldg_u32(src + ip))] = (TableT)ip;
+                if (lane == 0) table[hash4(ld_u32x(src + ip))] = (TableT)ip;
                 ip += 1;
             }
             __syncwarp();

@@ -254,17 +254,40 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                     dep = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
                 }
                 const bool lng = myML > LONG_SEQ;
+                // a short self-overlapping match with offset < 8 repeats a pattern that fits one register pair
+                const bool tiny = !lng && off < 8 && off < myML;
                 bool pending = valid;
                 uint32_t pm = __ballot_sync(FULL, pending);
                 while (pm) {
                     const bool go = pending && (pm & dep) == 0;
-                    const uint32_t nm = (go && !lng) ? myML : 0u;
-                    const uint32_t mx = __reduce_max_sync(FULL, nm);
                     uint8_t* md = dst + ms;
                     const uint8_t* msrc = dst + s;
-#pragma unroll 4
-                    for (uint32_t i = 0; i < mx; i++)
-                        if (i < nm) md[i] = msrc[i];
+                    {   // 8 bytes at a time: all loads of a chunk are issued before its stores.  Safe for a
+                        // self-overlapping match with offset >= 8: a chunk only reads bytes of earlier chunks.
+                        const uint32_t nm = (go && !lng && !tiny) ? myML : 0u;
+                        const uint32_t mx = __reduce_max_sync(FULL, nm);
+                        for (uint32_t i0 = 0; i0 < mx; i0 += 8) {
+                            uint32_t r[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (i0 + u < nm) r[u] = msrc[i0 + u];
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (i0 + u < nm) md[i0 + u] = (uint8_t)r[u];
+                        }
+                    }
+                    if (__ballot_sync(FULL, go && tiny)) {
+                        if (go && tiny) {
+                            uint64_t pat = 0;
+                            for (uint32_t i = 0; i < off; i++) pat |= (uint64_t)msrc[i] << (8 * i);
+                            uint32_t j = 0;
+                            for (uint32_t i = 0; i < myML; i++) {
+                                md[i] = (uint8_t)(pat >> (8 * j));
+                                j = (j + 1 == off) ? 0u : j + 1;
+                            }
+                        }
+                        __syncwarp();
+                    }
                     uint32_t gm = __ballot_sync(FULL, go && lng);
                     while (gm) {
                         const int j = __ffs(gm) - 1;
