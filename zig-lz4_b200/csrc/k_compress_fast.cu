@@ -64,7 +64,7 @@ __device__ __forceinline__ void write_len_ext(uint8_t* p, uint32_t L, uint32_t c
 }
 
 template <typename TableT>
-__device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
+__device__ void compress_block_general(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
                                TableT* table, uint32_t accel, uint32_t lane, uint32_t& olen, int& st) {
     st = ST_OK;
     olen = 0;
@@ -226,6 +226,225 @@ __device__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint
     olen = total;
 }
 
+// ------------------------------------------------------------------------------------------------
+// acceleration == 1 (compressDefault, every frame block): the lean path.
+//
+// With step == 1 the reference's iterations visit q, q+1, q+2, ... (p_j = q + j for the first
+// 65 iterations), and the position e = q - 1 is the one put() after the previous match (:438-442).  So
+// the first window of a search is simply p = e + lane: lane 0 only inserts (never matches), lanes 1..31
+// are iterations 1..31.  anchor == e, hence the literal run of a match found by lane L is L bytes long
+// and its bytes are the low bytes of the lanes' own 4-byte reads.
+//
+// Intra-window put() order without MATCH.ANY: every active lane writes its position into its bucket
+// and reads it back.  If every lane reads its own value the 32 buckets are distinct (88 % of windows):
+// the table values read before the writes are the candidates, lanes up to the match keep their write
+// (= their put()), later lanes restore what they read.  Otherwise everything is restored and the
+// general resolution (__match_any_sync) runs.
+template <typename TableT>
+__device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
+                                  TableT* table, uint32_t lane, uint32_t& olen, int& st) {
+    st = ST_OK;
+    olen = 0;
+    if (n == 0) return;                                          // :299
+    if (n > LZ4_MAX_INPUT_SIZE) { st = ST_INPUT_TOO_LARGE; return; }  // :296
+    uint32_t op = 0, anchor = 0;
+
+    if (n >= MFLIMIT + 1) {                                      // :302
+        {   // HashTable.init(), :307
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4* t4 = reinterpret_cast<uint4*>(table);
+            constexpr uint32_t NV = HASH_ENTRIES * sizeof(TableT) / 16;
+#pragma unroll 4
+            for (uint32_t i = lane; i < NV; i += 32) t4[i] = z;
+            __syncwarp();
+        }
+        const uint32_t lim = n - MFLIMIT;         // mflimitPlusOne, :313
+        const uint32_t mlimit = n - LASTLITERALS;  // matchLimit, :314
+        const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+        uint32_t e = 0;  // position put() before the search starts at e + 1 (0: nothing, table value 0 == empty)
+
+        while (e + 1 < lim) {                                    // :320 with ip == e + 1
+            if (lane == 0 && e + 512 < n) prefetch_l1(src + e + 512);
+            uint32_t mpos = 0, mcand = 0, LL = 0;
+            uint32_t litb = 0;      // short-form literal byte of this lane (window 0 only)
+            bool found = false, win0 = false;
+            {   // ---------------- window 0: p = e + lane ----------------
+                const uint32_t room = lim - e - 1;                       // lim - q >= 1
+                const uint32_t A = (room < 2 ? 2u : room) + 1;           // active lanes (iterations 1, 2 never exit)
+                const bool active = lane < A;
+                const uint32_t p = e + lane;
+                uint32_t v = 0, h = 0, old = 0;
+                if (active) { v = ld_u32x(src + p); h = hash4(v); old = table[h]; }
+                __syncwarp();
+                if (active) table[h] = (TableT)p;
+                __syncwarp();
+                bool clash = false;
+                if (active) clash = table[h] != (TableT)p;
+                const uint32_t cm = __ballot_sync(FULL, clash);
+                uint32_t cand = old;
+                uint32_t peers = 0;
+                if (cm) {                                                // rare: shared buckets inside the window
+                    if (active) table[h] = (TableT)old;
+                    peers = __match_any_sync(FULL, active ? h : (0x80000000u | lane));
+                    const uint32_t prev = peers & lt;
+                    const int sl = prev ? 31 - __clz(prev) : (int)lane;
+                    const uint32_t pp = __shfl_sync(FULL, p, sl);
+                    if (prev) cand = pp;
+                }
+                bool valid = active && lane > 0 && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;  // :345-347
+                if (valid) {
+                    const uint8_t* cp = src + cand;
+                    if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && cand + 19 < n) touch_sector(cp + 19);
+                    valid = (ld_u32x(cp) == v);                          // :348
+                }
+                const uint32_t vm = __ballot_sync(FULL, valid);
+                const uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
+                if (cm) {
+                    const uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
+                    const bool commit = active && lane <= L && ((peers & gt & le) == 0);
+                    __syncwarp();
+                    if (commit) table[h] = (TableT)p;
+                } else if (active && lane > L) {
+                    table[h] = (TableT)old;                              // iterations after the match never ran
+                }
+                __syncwarp();
+                if (vm) {
+                    found = true; win0 = true;
+                    mpos = e + L; LL = L;
+                    mcand = __shfl_sync(FULL, cand, L);
+                    litb = __shfl_up_sync(FULL, v, 1) & 0xFFu;           // lane i (1..LL) holds src[e + i - 1]
+                } else if (A < 32) {
+                    break;                                               // -> finishCompression, :335-338
+                }
+            }
+            if (!found) {
+                // ---------------- later windows (no match within 31 bytes): general schedule, a0 == 1 ----------------
+                const uint32_t q = e + 1;
+                uint32_t j0 = 31;
+                for (;;) {
+                    uint32_t j = j0 + lane;
+                    uint32_t x = j + 63, s = x >> 6;                 // j >= 2: reference iteration k = j + 64, x = a0 + k - 2
+                    uint32_t p = q + 1 + step_prefix(x);             // step_prefix(1) == 0
+                    bool can = (p + s <= lim);                       // :335
+                    uint32_t em = __ballot_sync(FULL, !can);
+                    uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;
+                    bool active = lane < E;
+                    uint32_t v = 0, h = 0x80000000u | lane, cand = 0;
+                    if (active) { v = ld_u32x(src + p); h = hash4(v); cand = table[h]; }
+                    uint32_t peers = __match_any_sync(FULL, h);
+                    uint32_t prev = peers & lt;
+                    int sl = prev ? 31 - __clz(prev) : (int)lane;
+                    uint32_t pp = __shfl_sync(FULL, p, sl);
+                    if (prev) cand = pp;
+                    bool valid = active && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;
+                    if (valid) valid = (ld_u32x(src + cand) == v);
+                    uint32_t vm = __ballot_sync(FULL, valid);
+                    uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
+                    uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
+                    bool commit = active && lane <= L && ((peers & gt & le) == 0);
+                    __syncwarp();
+                    if (commit) table[h] = (TableT)p;
+                    __syncwarp();
+                    if (vm) { mpos = __shfl_sync(FULL, p, L); mcand = __shfl_sync(FULL, cand, L); found = true; break; }
+                    if (E < 32) break;
+                    j0 += 32;
+                }
+                if (!found) break;
+                LL = mpos - anchor;                                      // :360
+            }
+
+            // ---------------- match extension, :401-413 ----------------
+            const uint32_t offset = mpos - mcand;                        // :395
+            uint32_t a = mpos + MINMATCH, b = mcand + MINMATCH, ml = 0;
+            {   // first 16 bytes on four lanes; most matches end here
+                uint32_t cnt = 4;
+                if (lane < 4) {
+                    const uint32_t al = a + 4 * lane;
+                    const uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+                    cnt = 0;
+                    if (nb) {
+                        const uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+                        const uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                        cnt = mm < nb ? mm : nb;
+                    }
+                }
+                const uint32_t stopm = __ballot_sync(FULL, cnt < 4);
+                if (stopm) {
+                    const uint32_t f = (uint32_t)__ffs(stopm) - 1;
+                    ml = 4 * f + __shfl_sync(FULL, cnt, f);
+                } else {
+                    ml = 16; a += 16; b += 16;
+                    for (;;) {
+                        uint32_t al = a + 4 * lane;
+                        uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+                        uint32_t c2 = 0;
+                        if (nb) {
+                            uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+                            uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                            c2 = mm < nb ? mm : nb;
+                        }
+                        uint32_t sm = __ballot_sync(FULL, c2 < 4);
+                        if (sm) {
+                            uint32_t f = (uint32_t)__ffs(sm) - 1;
+                            ml += 4 * f + __shfl_sync(FULL, c2, f);
+                            break;
+                        }
+                        ml += 128; a += 128; b += 128;
+                    }
+                }
+            }
+            const uint32_t mend = mpos + MINMATCH + ml;
+
+            // ---------------- emit sequence, :362-432 ----------------
+            if (LL < RUN_MASK && ml < ML_MASK) {
+                // short form: token | literals | offset = LL + 3 <= 17 bytes, one byte per lane
+                const uint32_t seq_end = op + LL + 3;
+                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // monotone in op: see DESIGN.md
+                uint32_t bv = (LL << 4) | ml;
+                if (lane >= 1 && lane <= LL) bv = win0 ? litb : (uint32_t)__ldg(src + anchor + lane - 1);
+                else if (lane == LL + 1) bv = offset;
+                else if (lane == LL + 2) bv = offset >> 8;
+                if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
+                op = seq_end;
+            } else {
+                const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+                const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+                const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }
+                uint8_t* o = dst + op;
+                if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
+                write_len_ext(o + 1, LL, nll, lane);
+                warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+                uint8_t* o2 = o + 1 + nll + LL;
+                if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
+                write_len_ext(o2 + 2, ml, nml, lane);
+                op = seq_end;
+            }
+            anchor = mend;                                       // :435
+            e = mend;                                            // put(e) is lane 0 of the next window (:438-442)
+        }
+    }
+
+    // ---------------- last literals: compressAsLiterals :449-482 / finishCompression :484-519 ----------------
+    const uint32_t LL = n - anchor;
+    const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+    const uint32_t total = op + 1 + nll + LL;
+    if (total > cap) { st = ST_OUTPUT_TOO_SMALL; return; }
+    uint8_t* o = dst + op;
+    if (lane == 0) o[0] = (uint8_t)((LL < 15 ? LL : 15u) << 4);
+    write_len_ext(o + 1, LL, nll, lane);
+    warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+    olen = total;
+}
+
+template <typename TableT>
+__device__ __forceinline__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst,
+                                               uint32_t cap, TableT* table, uint32_t accel, uint32_t lane, uint32_t& olen,
+                                               int& st) {
+    if (accel <= 1) compress_block_a1<TableT>(src, n, dst, cap, table, lane, olen, st);  // :321 clamps 0 to 1
+    else compress_block_general<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
+}
+
 template <typename TableT>
 __global__ void __launch_bounds__(K1_THREADS) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                               int32_t* __restrict__ status, uint32_t nblocks,
@@ -260,23 +479,29 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     const bool small = max_len <= 65536;
-    const size_t smem = (size_t)K1_WARPS * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
+    // shared memory per SM is what bounds the blocks in flight (227 KiB, 1 KiB reserved per CTA):
+    //   u16 tables (8 KiB / warp):  CTAs of 3 warps, 9 per SM -> 27 blocks in flight
+    //   u32 tables (16 KiB / warp): CTAs of 1 warp, 13 per SM -> 13 blocks in flight
+    const int warps = small ? 3 : 1;
+    const int ctas_per_sm = small ? 9 : 13;
+    const size_t smem = (size_t)warps * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_compress_fast<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              K1_WARPS * HASH_ENTRIES * (int)sizeof(uint32_t));
         cudaFuncSetAttribute(k_compress_fast<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              K1_WARPS * HASH_ENTRIES * (int)sizeof(uint16_t));
+        cudaFuncSetAttribute(k_compress_fast<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_compress_fast<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_done = true;
     }
-    const int ctas_per_sm = small ? 7 : 3;  // 227 KiB / (32 | 64) KiB
-    uint32_t want = (nblocks + K1_WARPS - 1) / K1_WARPS;
+    uint32_t want = (nblocks + warps - 1) / warps;
     uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
     uint32_t grid = want < maxg ? want : maxg;
     if (small)
-        k_compress_fast<uint16_t><<<grid, K1_THREADS, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        k_compress_fast<uint16_t><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     else
-        k_compress_fast<uint32_t><<<grid, K1_THREADS, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        k_compress_fast<uint32_t><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     count_launch();
     return cudaGetLastError();
 }
