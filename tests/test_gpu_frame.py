@@ -244,3 +244,88 @@ def test_device_pointer_frame_and_shards(z, oracle, ctx):
     o0 = torch.empty(cut + 64, dtype=torch.uint8, device="cuda")
     assert ctx.decompress_blocks_dev(b0.data_ptr(), s0, o0.data_ptr(), cut, 65536, True, s) == cut
     assert torch.equal(o0[:cut], src[:cut])
+
+
+def _same_frame_result(z, oracle, frame, cap):
+    try:
+        want = (0, oracle.decompress_frame(frame, cap))
+    except oracle.OracleError as e:
+        want = (e.code, None)
+    try:
+        got = (0, z.lz4f.decompressFrame(frame, cap))
+    except z.B2Error as e:
+        got = (e.code, None)
+    assert got[0] == want[0], (oracle.status_name(want[0]), z.status_name(got[0]))
+    if want[0] == 0:
+        assert got[1] == want[1]
+    return want[0]
+
+
+def test_parallel_index_adversarial_payloads(z, oracle):
+    """the parallel block index (k_index.cu) tests every byte position as a possible header: payloads made of
+    plausible header words (small u32s, raw flags, zeros) must not derail it, and a stored block larger than
+    the frame's block size (accepted by the reference, src/lz4f.zig:578-587) must take the serial fallback"""
+    rng = np.random.default_rng(11)
+    hdr64k = bytes.fromhex("04224d186040" + "82")              # independent blocks, 64 KiB, no checksums
+    hdr_bc = bytes.fromhex("04224d187040") + b"\x00"            # + block checksums; header checksum fixed below
+    hdr_bc = hdr_bc[:6] + bytes([(oracle.xxh32(hdr_bc[4:6]) >> 8) & 0xFF])
+
+    def raw_block(payload, bc=False):
+        rec = (len(payload) | 0x80000000).to_bytes(4, "little") + payload
+        if bc:
+            rec += oracle.xxh32(payload).to_bytes(4, "little")
+        return rec
+
+    small_words = rng.integers(1, 3000, size=15000, dtype=np.uint32).tobytes()            # every word looks like a header
+    flagged = (rng.integers(0, 70000, size=15000, dtype=np.uint32) | 0x80000000).astype(np.uint32).tobytes()
+    zeros = bytes(60000)
+    mixed = b"".join([small_words[:20000], zeros[:5000], flagged[:20000], b"\x01\x00\x00\x00" * 3000])
+    for bc, hdr in ((False, hdr64k), (True, hdr_bc)):
+        payloads = [small_words[:60000], flagged[:60000], zeros, mixed[:65536], b"\x04\x00\x00\x00\x00\x00\x00\x00" * 4000]
+        frame = bytearray(hdr)
+        total = b""
+        for pl in payloads * 3:
+            c = oracle.compress_fast(pl)
+            if len(c) < len(pl) and len(total) % 2 == 0:
+                frame += len(c).to_bytes(4, "little") + c
+                if bc:
+                    frame += oracle.xxh32(c).to_bytes(4, "little")
+            else:
+                frame += raw_block(pl, bc)
+            total += pl
+        frame += b"\0\0\0\0"
+        assert _same_frame_result(z, oracle, bytes(frame), len(total)) == 0
+        _same_frame_result(z, oracle, bytes(frame[:-4]), len(total))          # no end mark: loop runs off the end
+        _same_frame_result(z, oracle, bytes(frame[:-9]), len(total))          # truncated last record
+        _same_frame_result(z, oracle, bytes(frame[:len(frame) // 2]), len(total))
+    # a stored block above the block size: the candidate filter rejects it, the serial walk accepts it
+    big = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+    frame = hdr64k + raw_block(b"abc" * 100) + raw_block(big) + raw_block(b"tail") + b"\0\0\0\0"
+    assert _same_frame_result(z, oracle, frame, 80000) == 0
+    # empty body, body that is only an end mark, garbage after the header
+    for body in (b"", b"\0\0\0\0", b"\0\0\0", b"\xff\xff\xff\x7f", b"\x05\x00\x00\x80abc"):
+        _same_frame_result(z, oracle, hdr64k + body, 100)
+
+
+def test_parallel_index_equals_serial_walk(z, oracle, ctx):
+    """same frame through the parallel index and (B2_SERIAL_WALK=1, separate process) the serial header chase"""
+    import os
+    import subprocess
+    import sys
+    from zig_lz4_b200 import datagen
+    data = datagen.generate(24 << 20, mode=4).tobytes()
+    zp, op = both_prefs(z, oracle, dict(block_mode=1, block_checksum=1, content_checksum=1), len(data))
+    f = z.lz4f.compressFrame(data, zp)
+    assert z.lz4f.decompressFrame(f, len(data)) == data
+    code = ("import sys; sys.path.insert(0, %r); import zig_lz4_b200 as z; f = open(sys.argv[1], 'rb').read(); "
+            "d = z.lz4f.decompressFrame(f, int(sys.argv[2])); import hashlib; print(hashlib.sha1(d).hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import hashlib
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".lz4") as tf:
+        tf.write(f); tf.flush()
+        env = dict(os.environ, B2_SERIAL_WALK="1")
+        out = subprocess.run([sys.executable, "-c", code % root, tf.name, str(len(data))], env=env, capture_output=True,
+                             text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip() == hashlib.sha1(data).hexdigest()

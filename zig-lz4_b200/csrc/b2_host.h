@@ -59,6 +59,7 @@ struct HostResults {
     uint32_t content_sum;
     uint32_t pad;
     XxhState xxh;
+    uint64_t idx_nodes;
 };
 
 }  // namespace b2
@@ -77,16 +78,18 @@ struct b2lz4_ctx {
     float phase_ms[5] = {0, 0, 0, 0, 0};
     // workspace
     b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, hc_work;
+    b2::DevBuf idx_tiles, idx_pos, idx_jump;   // parallel frame index scratch
     b2::DevBuf stage_in[2], stage_out[2], stage_aux;
     b2::PinBuf results, pin_aux;
     // layout of `small` (device): ticket u32 @0, FrameTotals @64, WalkResult @128, DecodeSummary @192,
-    // content_sum u32 @256, XxhState @320
+    // content_sum u32 @256, XxhState @320, index node count u64 @512
     uint32_t* d_ticket() const { return small.as<uint32_t>(); }
     b2::FrameTotals* d_totals() const { return reinterpret_cast<b2::FrameTotals*>(small.as<uint8_t>() + 64); }
     b2::WalkResult* d_walk() const { return reinterpret_cast<b2::WalkResult*>(small.as<uint8_t>() + 128); }
     b2::DecodeSummary* d_summary() const { return reinterpret_cast<b2::DecodeSummary*>(small.as<uint8_t>() + 192); }
     uint32_t* d_content_sum() const { return reinterpret_cast<uint32_t*>(small.as<uint8_t>() + 256); }
     b2::XxhState* d_xxh() const { return reinterpret_cast<b2::XxhState*>(small.as<uint8_t>() + 320); }
+    uint64_t* d_idx_nodes() const { return reinterpret_cast<uint64_t*>(small.as<uint8_t>() + 512); }
     b2::HostResults* h() const { return results.as<b2::HostResults>(); }
     size_t workspace_bytes() const;
 };

@@ -73,6 +73,17 @@ struct WalkResult {
 cudaError_t launch_walk(const uint8_t* frame, uint64_t n, uint64_t start, uint32_t block_checksum, uint64_t* off,
                         uint32_t* hdr, uint32_t capacity, WalkResult* res, cudaStream_t stream);
 
+// K7' — parallel frame index (k_index.cu): candidate headers -> links -> jump tables -> ordered records.
+// res->terminal == 3 means "a header above `bound` sits on the chain": fall back to launch_walk.
+uint32_t index_tiles(const uint8_t* frame, uint64_t n);
+uint32_t index_levels(uint32_t n_nodes);
+cudaError_t launch_index_candidates(const uint8_t* frame, uint64_t n, uint64_t start, uint32_t bound, uint32_t block_checksum,
+                                    uint32_t* tile_count, uint64_t* tile_base, uint16_t* masks, uint64_t* pos,
+                                    uint64_t capacity, uint64_t* n_nodes, cudaStream_t stream);
+cudaError_t launch_index_resolve(const uint8_t* frame, uint64_t n, uint64_t start, uint32_t bound, uint32_t block_checksum,
+                                 const uint64_t* pos, uint32_t n_nodes, uint32_t* jump, uint64_t* off, uint32_t* hdr,
+                                 uint32_t capacity, WalkResult* res, cudaStream_t stream);
+
 struct DecodeSummary {
     uint32_t first_bad;        // first block index with a checksum / decode problem (0xFFFFFFFF none)
     int32_t bad_kind;          // 1 = block checksum mismatch, 2 = decode error, 3 = raw block no room

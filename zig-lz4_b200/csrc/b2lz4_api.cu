@@ -67,7 +67,7 @@ using namespace b2;
 
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
-               out_len.cap + hc_work.cap + stage_aux.cap;
+               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap;
     for (int i = 0; i < 2; i++) t += stage_in[i].cap + stage_out[i].cap;
     return t;
 }
@@ -132,7 +132,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->slots, &c->csize, &c->status, &c->sums, &c->rec_off, &c->small, &c->walk_off, &c->walk_hdr,
-                      &c->out_len, &c->hc_work, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1],
+                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1],
                       &c->stage_aux};
     for (auto* b : bufs) b->release();
     c->results.release();
@@ -493,6 +493,57 @@ static int decode_blocks_dev(b2lz4_ctx* c, const uint8_t* src, uint64_t n, const
     return B2LZ4_OK;
 }
 
+// Block index of a frame body: offsets and header words of its records, in order (reference loop control
+// src/lz4f.zig:563-591).  Built in parallel (k_index.cu); the serial header chase (k_walk) only runs when
+// the candidate list is implausibly long or a header above `bound` sits on the chain.
+static int build_block_index(b2lz4_ctx* c, const uint8_t* src, uint64_t n, uint64_t start, uint32_t bound, bool bc,
+                             cudaStream_t s, WalkResult* wout) {
+    static const bool force_serial = getenv("B2_SERIAL_WALK") != nullptr;
+    if (!force_serial && n > start) {
+        const uint32_t ntiles = index_tiles(src, n);
+        uint64_t cap_nodes = (n - start) / 64 + 4096;
+        if (cap_nodes > (1u << 20)) cap_nodes = 1u << 20;
+        // per tile: count u32, base u64; per 16-byte chunk: candidate mask u16
+        const size_t tiles_bytes = (((size_t)ntiles * 4 + 15) & ~size_t(15)) + (size_t)ntiles * 8;
+        B2_CUDA(c->idx_tiles.ensure(tiles_bytes + (size_t)ntiles * (65536 / 16) * 2 + 64));
+        B2_CUDA(c->idx_pos.ensure((size_t)cap_nodes * 8));
+        uint32_t* tile_count = c->idx_tiles.as<uint32_t>();
+        uint64_t* tile_base = reinterpret_cast<uint64_t*>(c->idx_tiles.as<uint8_t>() + (((size_t)ntiles * 4 + 15) & ~size_t(15)));
+        uint16_t* masks = reinterpret_cast<uint16_t*>(c->idx_tiles.as<uint8_t>() + ((tiles_bytes + 15) & ~size_t(15)));
+        B2_CUDA(launch_index_candidates(src, n, start, bound, bc ? 1 : 0, tile_count, tile_base, masks,
+                                        c->idx_pos.as<uint64_t>(), cap_nodes, c->d_idx_nodes(), s));
+        B2_CUDA(cudaMemcpyAsync(&c->h()->idx_nodes, c->d_idx_nodes(), 8, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        const uint64_t nn = c->h()->idx_nodes;
+        if (nn <= cap_nodes) {
+            const uint32_t levels = index_levels((uint32_t)nn);
+            B2_CUDA(c->idx_jump.ensure((size_t)levels * (nn + 1) * 4));
+            B2_CUDA(c->walk_off.ensure((size_t)(nn + 1) * 8));
+            B2_CUDA(c->walk_hdr.ensure((size_t)(nn + 1) * 4));
+            B2_CUDA(launch_index_resolve(src, n, start, bound, bc ? 1 : 0, c->idx_pos.as<uint64_t>(), (uint32_t)nn,
+                                         c->idx_jump.as<uint32_t>(), c->walk_off.as<uint64_t>(), c->walk_hdr.as<uint32_t>(),
+                                         (uint32_t)nn, c->d_walk(), s));
+            B2_CUDA(cudaMemcpyAsync(&c->h()->walk, c->d_walk(), sizeof(WalkResult), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+            if (c->h()->walk.terminal != 3) { *wout = c->h()->walk; return B2LZ4_OK; }
+        }
+    }
+    uint64_t capacity = (n - (n > start ? start : n)) / 256 + 1024;
+    if (capacity > 0x7FFFFFFFull) capacity = 0x7FFFFFFFull;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        B2_CUDA(c->walk_off.ensure((size_t)capacity * 8));
+        B2_CUDA(c->walk_hdr.ensure((size_t)capacity * 4));
+        B2_CUDA(launch_walk(src, n, start, bc ? 1 : 0, c->walk_off.as<uint64_t>(), c->walk_hdr.as<uint32_t>(), (uint32_t)capacity,
+                            c->d_walk(), s));
+        B2_CUDA(cudaMemcpyAsync(&c->h()->walk, c->d_walk(), sizeof(WalkResult), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        if (c->h()->walk.nblocks <= capacity) break;
+        capacity = c->h()->walk.nblocks;
+    }
+    *wout = c->h()->walk;
+    return B2LZ4_OK;
+}
+
 }  // namespace
 int b2_decompress_dev_impl(b2lz4_ctx* c, const void* srcv, size_t n, void* dstv, size_t cap, size_t* out, cudaStream_t s) {
     if (!out) return B2LZ4F_ERR_PARAMETER_NULL;
@@ -518,20 +569,10 @@ int b2_decompress_dev_impl(b2lz4_ctx* c, const void* srcv, size_t n, void* dstv,
     if (rc) return rc;
     size_t bs; block_size_of(info.block_size_id, bs);
     const bool bc = info.block_checksum == 1, cc = info.content_checksum == 1;
-    // K7: walk the block-header chain on the device (serial)
-    uint64_t capacity = (n - hsize) / 256 + 1024;
-    if (capacity > 0x7FFFFFFFull) capacity = 0x7FFFFFFFull;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        B2_CUDA(c->walk_off.ensure((size_t)capacity * 8));
-        B2_CUDA(c->walk_hdr.ensure((size_t)capacity * 4));
-        B2_CUDA(launch_walk(src, n, hsize, bc ? 1 : 0, c->walk_off.as<uint64_t>(), c->walk_hdr.as<uint32_t>(), (uint32_t)capacity,
-                            c->d_walk(), s));
-        B2_CUDA(cudaMemcpyAsync(&c->h()->walk, c->d_walk(), sizeof(WalkResult), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(cudaStreamSynchronize(s));
-        if (c->h()->walk.nblocks <= capacity) break;
-        capacity = c->h()->walk.nblocks;
-    }
-    const WalkResult w = c->h()->walk;
+    // K7': the block index (parallel; SURVEY F12 describes the serial chain it replaces)
+    WalkResult w;
+    rc = build_block_index(c, src, n, hsize, (uint32_t)bs, bc, s, &w);
+    if (rc) return rc;
     T.mark(1);
     uint64_t total = 0;
     rc = decode_blocks_dev(c, src, n, c->walk_off.as<uint64_t>(), c->walk_hdr.as<uint32_t>(), w.nblocks, w.terminal, dst, cap,
@@ -587,19 +628,8 @@ int b2lz4f_decompress_blocks_dev(b2lz4_ctx* c, const void* srcv, size_t n, void*
     const uint8_t* src = (const uint8_t*)srcv;
     Timer T{c, s, c->timing};
     T.mark(0);
-    uint64_t capacity = n / 256 + 1024;
-    if (capacity > 0x7FFFFFFFull) capacity = 0x7FFFFFFFull;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        B2_CUDA(c->walk_off.ensure((size_t)capacity * 8));
-        B2_CUDA(c->walk_hdr.ensure((size_t)capacity * 4));
-        B2_CUDA(launch_walk(src, n, 0, block_checksum ? 1 : 0, c->walk_off.as<uint64_t>(), c->walk_hdr.as<uint32_t>(),
-                            (uint32_t)capacity, c->d_walk(), s));
-        B2_CUDA(cudaMemcpyAsync(&c->h()->walk, c->d_walk(), sizeof(WalkResult), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(cudaStreamSynchronize(s));
-        if (c->h()->walk.nblocks <= capacity) break;
-        capacity = c->h()->walk.nblocks;
-    }
-    const WalkResult w = c->h()->walk;
+    WalkResult w;
+    { int rc0 = build_block_index(c, src, n, 0, (uint32_t)block_size, block_checksum != 0, s, &w); if (rc0) return rc0; }
     T.mark(1);
     uint64_t total = 0;
     // a body has no end mark: running off the end (terminal 1) is the normal exit
