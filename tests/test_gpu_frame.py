@@ -329,3 +329,59 @@ def test_parallel_index_equals_serial_walk(z, oracle, ctx):
                              text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip() == hashlib.sha1(data).hexdigest()
+
+
+@pytest.fixture
+def small_pipeline_chunks(monkeypatch):
+    """makes the host-pointer frame calls pipeline (upload | kernels | download on three streams) with 24-block
+    chunks, so that frames of a few MiB go through the chunked path"""
+    monkeypatch.setenv("B2_PIPE_BLOCKS", "24")
+    yield
+    monkeypatch.delenv("B2_PIPE_BLOCKS", raising=False)
+
+
+@pytest.mark.parametrize("kw", PREFS + [dict(compression_level=9, block_checksum=1, content_checksum=1)])
+def test_pipelined_host_frames(z, oracle, small_pipeline_chunks, kw):
+    """chunked, double-buffered host path == one-shot oracle frame, for every preference combination"""
+    from zig_lz4_b200 import datagen
+    bsid = kw.get("block_size_id", 0)
+    n = {0: 9, 5: 30, 6: 90, 7: 300}[bsid] * (1 << 20) + 12345
+    if kw.get("compression_level"):
+        n = 7 * (1 << 20) + 99
+    data = datagen.generate(n, mode=4, seed=n).tobytes()
+    zp, op = both_prefs(z, oracle, kw, len(data))
+    want = oracle.compress_frame(data, op, threads=8)
+    got = z.lz4f.compressFrame(data, zp)
+    assert len(got) == len(want)
+    assert got == want
+    assert z.lz4f.decompressFrame(got, len(data)) == data
+    assert z.lz4f.decompressFrame(got, len(data) + 777) == data
+
+
+def test_pipelined_host_decode_falls_back_exactly(z, oracle, small_pipeline_chunks):
+    """anything unusual inside a chunk (corruption, short output, short blocks) must give the oracle's result"""
+    from zig_lz4_b200 import datagen
+    data = datagen.generate(6 << 20, mode=4, seed=5).tobytes()
+    zp, op = both_prefs(z, oracle, dict(block_mode=1, block_checksum=1, content_checksum=1), len(data))
+    f = z.lz4f.compressFrame(data, zp)
+    rng = np.random.default_rng(8)
+    for _ in range(6):
+        bad = bytearray(f)
+        bad[int(rng.integers(7, len(bad)))] ^= int(rng.integers(1, 256))
+        _same_frame_result(z, oracle, bytes(bad), len(data))
+    for cap in (len(data) - 1, len(data) - 65536, 3 << 20, 65536 * 30 + 1):
+        _same_frame_result(z, oracle, f, cap)
+    _same_frame_result(z, oracle, f[:-4], len(data))
+    _same_frame_result(z, oracle, f[:len(f) - 70000], len(data))
+    # foreign layout: short blocks in the middle of a long frame
+    zp2, op2 = both_prefs(z, oracle, dict(block_mode=1), len(data))
+    parts = [data[i:i + 50000] for i in range(0, 4 << 20, 50000)]
+    frame = bytearray(bytes.fromhex("04224d186040" + "82"))
+    for pt in parts:
+        cpt = oracle.compress_fast(pt)
+        if len(cpt) < len(pt):
+            frame += len(cpt).to_bytes(4, "little") + cpt
+        else:
+            frame += (len(pt) | 0x80000000).to_bytes(4, "little") + pt
+    frame += b"\0\0\0\0"
+    assert _same_frame_result(z, oracle, bytes(frame), 5 << 20) == 0

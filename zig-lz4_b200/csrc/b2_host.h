@@ -60,6 +60,8 @@ struct HostResults {
     uint32_t pad;
     XxhState xxh;
     uint64_t idx_nodes;
+    FrameTotals pipe_totals[4];      // host-pointer pipeline: one slot per chunk in flight
+    DecodeSummary pipe_summary[4];
 };
 
 }  // namespace b2
@@ -99,3 +101,6 @@ int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, siz
                          size_t* out, cudaStream_t s, bool body_only);
 int b2_decompress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out, cudaStream_t s);
 int b2_default_ctx(b2lz4_ctx** out);
+int b2_enqueue_body(b2lz4_ctx* c, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body, cudaStream_t s,
+                    bool timing);
+int b2_hc_supported(int level);

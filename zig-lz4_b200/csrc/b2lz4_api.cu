@@ -65,6 +65,8 @@ static int hc_nb_searches(int level) {
 
 using namespace b2;
 
+int b2_hc_supported(int level) { return hc_nb_searches(level) >= 0 ? 1 : 0; }
+
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
                out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap;
@@ -331,6 +333,29 @@ static int encode_blocks_to_slots(b2lz4_ctx* c, const void* src, size_t n, size_
 }
 
 }  // namespace
+// Enqueues block codec -> block checksums -> record scan -> assembly for the blocks of [src, src+n) (device)
+// into `body` (device) on stream s.  Nothing is synchronised; the totals end up in c->d_totals().
+int b2_enqueue_body(b2lz4_ctx* c, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body, cudaStream_t s,
+                    bool timing) {
+    const uint32_t nb = (uint32_t)((n + bs - 1) / bs);
+    Timer T{c, s, timing};
+    if (nb) { int rc = encode_blocks_to_slots(c, src, n, bs, level, nb, s); if (rc) return rc; }
+    else { B2_CUDA(c->csize.ensure(4)); B2_CUDA(c->status.ensure(4)); }
+    T.mark(1);
+    const size_t stride = slot_stride_for(bs);
+    BlockSet slots = regular_in(c->slots.p, stride, (uint64_t)nb * stride);
+    BlockSet raw = regular_in(src, bs, n);
+    B2_CUDA(c->sums.ensure((size_t)nb * 4 + 4));
+    if (bc && nb) B2_CUDA(launch_xxh32_stored(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), nb, s));
+    T.mark(2);
+    B2_CUDA(c->rec_off.ensure(((size_t)nb + 1) * 8));
+    B2_CUDA(launch_scan_records(c->csize.as<uint32_t>(), c->status.as<int32_t>(), nb, bs, n, bc ? 1 : 0,
+                                c->rec_off.as<uint64_t>(), c->d_totals(), s));
+    if (nb) B2_CUDA(launch_assemble(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), c->rec_off.as<uint64_t>(),
+                                    body, nb, bc ? 1 : 0, c->num_sms, s));
+    return B2LZ4_OK;
+}
+
 // Frame (or body-only) compression of a device buffer.  Enqueues everything on `s`, syncs once.
 int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,
                              size_t* out, cudaStream_t s, bool body_only) {
@@ -376,20 +401,7 @@ int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, siz
         if (c->timing) cudaEventRecord(c->ev_t[6], c->side);
         B2_CUDA(cudaEventRecord(c->ev_join, c->side));
     }
-    if (nb) { int rc = encode_blocks_to_slots(c, src, n, bs, level, nb, s); if (rc) return rc; }
-    else { B2_CUDA(c->csize.ensure(4)); B2_CUDA(c->status.ensure(4)); }
-    T.mark(1);
-    const size_t stride = slot_stride_for(bs);
-    BlockSet slots = regular_in(c->slots.p, stride, (uint64_t)nb * stride);
-    BlockSet raw = regular_in(src, bs, n);
-    B2_CUDA(c->sums.ensure((size_t)nb * 4 + 4));
-    if (bc && nb) B2_CUDA(launch_xxh32_stored(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), nb, s));
-    T.mark(2);
-    B2_CUDA(c->rec_off.ensure(((size_t)nb + 1) * 8));
-    B2_CUDA(launch_scan_records(c->csize.as<uint32_t>(), c->status.as<int32_t>(), nb, bs, n, bc ? 1 : 0,
-                                c->rec_off.as<uint64_t>(), c->d_totals(), s));
-    if (nb) B2_CUDA(launch_assemble(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), c->rec_off.as<uint64_t>(),
-                                    d8 + hsize, nb, bc ? 1 : 0, c->num_sms, s));
+    { int rc = b2_enqueue_body(c, src, n, bs, level, bc, d8 + hsize, s, c->timing); if (rc) return rc; }
     if (!body_only) {
         if (cc) B2_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
         B2_CUDA(launch_finalize(d8, hsize, c->d_totals(), cc ? c->d_content_sum() : nullptr, s));

@@ -6,6 +6,7 @@
 // The host side only moves bytes (H2D / D2H) and keeps the < blockSize tail of a stream; all codec
 // and checksum work runs in the kernels.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "b2_host.h"
@@ -48,18 +49,11 @@ static int download(b2lz4_ctx* c, void* h, const void* d, size_t n, cudaStream_t
     return B2LZ4_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int b2lz4f_compress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,
-                              size_t* out) {
-    if (!c || !out) return B2LZ4F_ERR_PARAMETER_NULL;
-    *out = 0;
-    const size_t bound = b2lz4f_compress_frame_bound(n, prefs);
-    if (cap < bound) return B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL;   // src/lz4f.zig:363-366
-    std::lock_guard<std::recursive_mutex> lk(c->mu);
-    B2_CUDA(cudaSetDevice(c->device));
+// ---------------------------------------------------------------- one-shot (unpipelined) host paths
+// Whole input up, one device call, whole output down.  Exact reference semantics in every corner; the
+// pipelined paths below fall back to these whenever something is unusual.
+static int compress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t bound, const b2lz4f_prefs* prefs,
+                                 size_t* out) {
     cudaStream_t s = c->stream;
     B2_CUDA(c->stage_in[0].ensure(n + 16));
     B2_CUDA(c->stage_out[0].ensure(bound + 16));
@@ -75,11 +69,7 @@ int b2lz4f_compress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst
     return B2LZ4_OK;
 }
 
-int b2lz4f_decompress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out) {
-    if (!c || !out) return B2LZ4F_ERR_PARAMETER_NULL;
-    *out = 0;
-    std::lock_guard<std::recursive_mutex> lk(c->mu);
-    B2_CUDA(cudaSetDevice(c->device));
+static int decompress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out) {
     cudaStream_t s = c->stream;
     B2_CUDA(c->stage_in[0].ensure(n + 16));
     B2_CUDA(c->stage_out[0].ensure(cap + 16));
@@ -93,6 +83,282 @@ int b2lz4f_decompress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* d
     B2_CUDA(cudaStreamSynchronize(s));
     *out = produced;
     return B2LZ4_OK;
+}
+
+// ---------------------------------------------------------------- pipelined host paths
+// The frame is cut into chunks of whole blocks.  Three streams work on different chunks at the same
+// time: copy_in uploads chunk k+1, the compute stream runs the kernels of chunk k, copy_out downloads
+// chunk k-1.  Input and output are double-buffered on the device (2 x chunk), so the workspace no longer
+// grows with the frame.  PCIe moves N + C bytes each way per round trip; the kernels hide behind that.
+// A chunk must hold enough blocks to fill the GPU (one warp per block, ~4000 warps resident), so chunks
+// are sized in blocks: 4096 blocks, at most 256 MiB of raw data; frames whose block size leaves fewer
+// than 1024 blocks per chunk (1 MiB / 4 MiB blocks) and frames shorter than three chunks take the
+// one-shot path.  B2_PIPE_BLOCKS overrides the block count (tests use it to pipeline small frames).
+constexpr size_t PIPE_MAX_CHUNK = 256u << 20;
+static size_t pipe_blocks_for(size_t bs, bool* forced) {
+    const char* e = getenv("B2_PIPE_BLOCKS");
+    if (e && atol(e) > 0) { *forced = true; return (size_t)atol(e); }
+    *forced = false;
+    size_t blocks = 4096;
+    if (blocks * bs > PIPE_MAX_CHUNK) blocks = PIPE_MAX_CHUNK / bs;
+    return blocks;
+}
+static bool pipeline_applies(size_t raw_bytes, size_t bs, size_t* chunk_blocks) {
+    if (getenv("B2_NO_PIPELINE")) return false;
+    bool forced;
+    const size_t blocks = pipe_blocks_for(bs, &forced);
+    *chunk_blocks = blocks;
+    if (!forced && blocks < 1024) return false;
+    return raw_bytes > 2 * blocks * bs;
+}
+
+static inline uint32_t rd32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, uint8_t* dst, size_t cap,
+                                    const b2lz4f_prefs* prefs, size_t bs, size_t chunk_blocks, size_t* out) {
+    const bool bc = prefs->block_checksum == 1, cc = prefs->content_checksum == 1;
+    const int level = prefs->compression_level;
+    size_t hsize = 0;
+    { int rc = b2lz4f_write_frame_header(dst, cap, prefs, &hsize); if (rc) return rc; }      // src/lz4f.zig:369
+    const size_t chunk = chunk_blocks * bs;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    const size_t rec_bound = 4 + compress_bound(bs) + (bc ? 4 : 0);
+    const size_t out_bound = (chunk / bs) * rec_bound;
+    for (int b = 0; b < 2; b++) {
+        B2_CUDA(c->stage_in[b].ensure(chunk + 16));
+        B2_CUDA(c->stage_out[b].ensure(out_bound + 16));
+    }
+    cudaStream_t s = c->stream;
+    cudaEvent_t* ev_up = &c->ev_pipe[0];     // [2] chunk uploaded
+    cudaEvent_t* ev_done = &c->ev_pipe[2];   // [2] chunk computed (input buffer free, totals on the host)
+    cudaEvent_t* ev_down = &c->ev_pipe[4];   // [2] chunk downloaded (output buffer free)
+    cudaEvent_t* ev_cc = &c->ev_pipe[6];     // [2] content checksum consumed the chunk
+    if (cc) B2_CUDA(launch_xxh32_init(c->d_xxh(), 0, c->side));
+    size_t pos = hsize;
+    int err = B2LZ4_OK;
+    for (size_t k = 0; k <= nchunks; k++) {
+        if (k < nchunks) {                                   // ---- enqueue chunk k
+            const int b = (int)(k & 1);
+            const size_t o = k * chunk, len = std::min(chunk, n - o);
+            if (k >= 2) {                                    // buffers of chunk k-2 must be free again
+                B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_done[b], 0));
+                if (cc) B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_cc[b], 0));
+                B2_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
+            }
+            B2_CUDA(cudaMemcpyAsync(c->stage_in[b].p, src + o, len, cudaMemcpyHostToDevice, c->copy_in));
+            B2_CUDA(cudaEventRecord(ev_up[b], c->copy_in));
+            B2_CUDA(cudaStreamWaitEvent(s, ev_up[b], 0));
+            if (cc) {                                        // serial content chain, chunk after chunk
+                B2_CUDA(cudaStreamWaitEvent(c->side, ev_up[b], 0));
+                B2_CUDA(launch_xxh32_update(c->d_xxh(), c->stage_in[b].as<uint8_t>(), len, c->side));
+                B2_CUDA(cudaEventRecord(ev_cc[b], c->side));
+            }
+            int rc = b2_enqueue_body(c, c->stage_in[b].p, len, bs, level, bc, c->stage_out[b].as<uint8_t>(), s, false);
+            if (rc) { err = rc; break; }
+            B2_CUDA(cudaMemcpyAsync(&c->h()->pipe_totals[k & 3], c->d_totals(), sizeof(FrameTotals), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaEventRecord(ev_done[b], s));
+        }
+        if (k >= 1) {                                        // ---- retire chunk k-1: its size is known now
+            const int b = (int)((k - 1) & 1);
+            B2_CUDA(cudaEventSynchronize(ev_done[b]));
+            const FrameTotals t = c->h()->pipe_totals[(k - 1) & 3];
+            if (t.first_bad != 0xFFFFFFFFu) {                // mapCompressionError, src/lz4f.zig:144-149
+                err = t.bad_status == B2LZ4_ERR_OUTPUT_TOO_SMALL ? B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL : B2LZ4F_ERR_GENERIC;
+                break;
+            }
+            B2_CUDA(cudaMemcpyAsync(dst + pos, c->stage_out[b].p, t.body_bytes, cudaMemcpyDeviceToHost, c->copy_out));
+            B2_CUDA(cudaEventRecord(ev_down[b], c->copy_out));
+            pos += t.body_bytes;
+        }
+    }
+    if (err) { cudaStreamSynchronize(s); cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side); return err; }
+    if (cc) {
+        B2_CUDA(launch_xxh32_final(c->d_xxh(), c->d_content_sum(), c->side));
+        B2_CUDA(cudaMemcpyAsync(&c->h()->content_sum, c->d_content_sum(), 4, cudaMemcpyDeviceToHost, c->side));
+        B2_CUDA(cudaStreamSynchronize(c->side));
+    }
+    B2_CUDA(cudaStreamSynchronize(c->copy_out));
+    dst[pos] = dst[pos + 1] = dst[pos + 2] = dst[pos + 3] = 0;                                  // end mark, :433
+    pos += 4;
+    if (cc) {                                                                                    // :437-441
+        const uint32_t h = c->h()->content_sum;
+        dst[pos] = (uint8_t)h; dst[pos + 1] = (uint8_t)(h >> 8); dst[pos + 2] = (uint8_t)(h >> 16); dst[pos + 3] = (uint8_t)(h >> 24);
+        pos += 4;
+    }
+    *out = pos;
+    return B2LZ4_OK;
+}
+
+// Returns 1 if the frame was decoded, 0 if the caller must take the one-shot path (anything unusual),
+// < 0 never; errors of the CUDA runtime are reported through *rc_out.
+static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out,
+                                      int* rc_out) {
+    *rc_out = B2LZ4_OK;
+    b2lz4f_prefs info; size_t hsize = 0;
+    if (b2lz4f_parse_frame_header(src, n, &info, &hsize) != B2LZ4_OK) return 0;
+    size_t bs; if (!block_size_of(info.block_size_id, bs)) return 0;
+    const bool bc = info.block_checksum == 1, cc = info.content_checksum == 1;
+    const size_t tr = bc ? 4 : 0;
+    // block index: the header chain read straight from the caller's (host) frame, src/lz4f.zig:563-591
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> hdr;
+    off.reserve(n / 1024 + 16); hdr.reserve(n / 1024 + 16);
+    size_t p = hsize;
+    bool end_mark = false;
+    while (p < n) {
+        if (p + 4 > n) return 0;
+        const uint32_t h = rd32(src + p);
+        p += 4;
+        if (h == 0) { end_mark = true; break; }
+        const size_t sz = h & 0x7FFFFFFFu;
+        if (p + sz + tr > n || sz > bs) return 0;
+        off.push_back(p); hdr.push_back(h);
+        p += sz + tr;
+    }
+    if (!end_mark || off.empty() || off.size() > 0x7FFFFFFFull) return 0;
+    if (cc && p + 4 > n) return 0;
+    const size_t nb = off.size();
+    if (cap < (nb - 1) * bs + 1) return 0;                       // optimistic layout needs room for every block start
+    size_t chunk_blocks;
+    if (!pipeline_applies(nb * bs, bs, &chunk_blocks)) return 0;
+    std::vector<size_t> cfirst;                                  // first block of each chunk (+ sentinel)
+    for (size_t i = 0; i < nb; i += chunk_blocks) cfirst.push_back(i);
+    cfirst.push_back(nb);
+    const size_t nchunks = cfirst.size() - 1;
+    size_t max_in = 0, max_blocks = 0;
+    for (size_t k = 0; k < nchunks; k++) {
+        const size_t i0 = cfirst[k], i1 = cfirst[k + 1];
+        max_in = std::max(max_in, (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - (off[i0] - 4)));
+        max_blocks = std::max(max_blocks, i1 - i0);
+    }
+    cudaStream_t s = c->stream;
+    auto fail = [&](cudaError_t e, const char* what) { set_cuda_error(e, what); *rc_out = B2LZ4_ERR_CUDA; return 1; };
+#define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(_e, #expr); } while (0)
+    for (int b = 0; b < 2; b++) {
+        PIPE_CUDA(c->stage_in[b].ensure(max_in + 32));
+        PIPE_CUDA(c->stage_out[b].ensure(max_blocks * bs + 16));
+    }
+    PIPE_CUDA(c->walk_off.ensure(nb * 8));
+    PIPE_CUDA(c->walk_hdr.ensure(nb * 4));
+    PIPE_CUDA(c->out_len.ensure(nb * 4 + 4));
+    PIPE_CUDA(c->status.ensure(nb * 4 + 4));
+    PIPE_CUDA(c->sums.ensure(nb * 4 + 4));
+    // per-chunk relative offsets (each chunk's bytes land at the start of its staging buffer)
+    std::vector<uint64_t> rel(nb);
+    for (size_t k = 0; k < nchunks; k++) {
+        const uint64_t lo = off[cfirst[k]] - 4;
+        for (size_t i = cfirst[k]; i < cfirst[k + 1]; i++) rel[i] = off[i] - lo;
+    }
+    PIPE_CUDA(cudaMemcpyAsync(c->walk_off.p, rel.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    PIPE_CUDA(cudaMemcpyAsync(c->walk_hdr.p, hdr.data(), nb * 4, cudaMemcpyHostToDevice, s));
+    cudaEvent_t* ev_up = &c->ev_pipe[0];
+    cudaEvent_t* ev_done = &c->ev_pipe[2];
+    cudaEvent_t* ev_down = &c->ev_pipe[4];
+    cudaEvent_t* ev_cc = &c->ev_pipe[6];
+    if (cc) PIPE_CUDA(launch_xxh32_init(c->d_xxh(), 0, c->side));
+    bool unusual = false;
+    size_t total = 0;
+    for (size_t k = 0; k <= nchunks && !unusual; k++) {
+        if (k < nchunks) {
+            const int b = (int)(k & 1);
+            const size_t i0 = cfirst[k], i1 = cfirst[k + 1], cnt = i1 - i0;
+            const uint64_t lo = off[i0] - 4;
+            const size_t in_len = (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - lo);
+            if (k >= 2) {
+                PIPE_CUDA(cudaStreamWaitEvent(c->copy_in, ev_done[b], 0));
+                PIPE_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
+                if (cc) PIPE_CUDA(cudaStreamWaitEvent(s, ev_cc[b], 0));
+            }
+            PIPE_CUDA(cudaMemcpyAsync(c->stage_in[b].p, src + lo, in_len, cudaMemcpyHostToDevice, c->copy_in));
+            PIPE_CUDA(cudaEventRecord(ev_up[b], c->copy_in));
+            PIPE_CUDA(cudaStreamWaitEvent(s, ev_up[b], 0));
+            const uint64_t* d_off = c->walk_off.as<uint64_t>() + i0;
+            const uint32_t* d_hdr = c->walk_hdr.as<uint32_t>() + i0;
+            uint32_t* d_len = c->out_len.as<uint32_t>() + i0;
+            int32_t* d_st = c->status.as<int32_t>() + i0;
+            uint32_t* d_sum = c->sums.as<uint32_t>() + i0;
+            const uint8_t* d_in = c->stage_in[b].as<uint8_t>();
+            if (bc) PIPE_CUDA(launch_xxh32_ranges(d_in, d_off, d_hdr, d_sum, (uint32_t)cnt, s));
+            BlockSet in; in.base = d_in; in.off = d_off; in.len = d_hdr; in.stride = 0; in.total = 0; in.len_mask = 0x7FFFFFFFu;
+            const uint64_t out_room = std::min<uint64_t>((uint64_t)cnt * bs, cap - (uint64_t)i0 * bs);
+            OutSet o; o.base = c->stage_out[b].as<uint8_t>(); o.off = nullptr; o.cap = nullptr; o.stride = bs; o.total = out_room;
+            o.slot_cap = (uint32_t)bs;
+            PIPE_CUDA(launch_decompress(in, o, d_hdr, d_len, d_st, (uint32_t)cnt, nullptr, 0, c->d_ticket(), c->num_sms, s));
+            PIPE_CUDA(launch_decode_summary(d_len, d_st, d_sum, d_in, d_off, d_hdr, (uint32_t)cnt, (uint32_t)bs, bc ? 1 : 0,
+                                            c->d_summary(), s));
+            PIPE_CUDA(cudaMemcpyAsync(&c->h()->pipe_summary[k & 3], c->d_summary(), sizeof(DecodeSummary), cudaMemcpyDeviceToHost, s));
+            PIPE_CUDA(cudaEventRecord(ev_done[b], s));
+        }
+        if (k >= 1) {
+            const size_t kk = k - 1;
+            const int b = (int)(kk & 1);
+            PIPE_CUDA(cudaEventSynchronize(ev_done[b]));
+            const DecodeSummary sm = c->h()->pipe_summary[kk & 3];
+            const bool last = kk + 1 == nchunks;
+            const size_t cnt = cfirst[kk + 1] - cfirst[kk];
+            // every block of the chunk must be regular: no error, and exactly bs bytes unless it is the frame's last block
+            if (sm.first_bad != 0xFFFFFFFFu || !sm.layout_ok || (!last && sm.total != (uint64_t)cnt * bs)) { unusual = true; break; }
+            if (cc) {
+                PIPE_CUDA(cudaStreamWaitEvent(c->side, ev_done[b], 0));
+                PIPE_CUDA(launch_xxh32_update(c->d_xxh(), c->stage_out[b].as<uint8_t>(), sm.total, c->side));
+                PIPE_CUDA(cudaEventRecord(ev_cc[b], c->side));
+            }
+            PIPE_CUDA(cudaMemcpyAsync(dst + cfirst[kk] * bs, c->stage_out[b].p, sm.total, cudaMemcpyDeviceToHost, c->copy_out));
+            PIPE_CUDA(cudaEventRecord(ev_down[b], c->copy_out));
+            total = cfirst[kk] * bs + sm.total;
+        }
+    }
+    if (unusual) {
+        cudaStreamSynchronize(s); cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side);
+        return 0;
+    }
+    if (cc) {
+        PIPE_CUDA(launch_xxh32_final(c->d_xxh(), c->d_content_sum(), c->side));
+        PIPE_CUDA(cudaMemcpyAsync(&c->h()->content_sum, c->d_content_sum(), 4, cudaMemcpyDeviceToHost, c->side));
+        PIPE_CUDA(cudaStreamSynchronize(c->side));
+    }
+    PIPE_CUDA(cudaStreamSynchronize(c->copy_out));
+    PIPE_CUDA(cudaStreamSynchronize(s));
+#undef PIPE_CUDA
+    if (cc && rd32(src + p) != c->h()->content_sum) { *rc_out = B2LZ4F_ERR_CONTENT_CHECKSUM_INVALID; return 1; }   // :625-635
+    *out = total;
+    return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2lz4f_compress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,
+                              size_t* out) {
+    if (!c || !out) return B2LZ4F_ERR_PARAMETER_NULL;
+    *out = 0;
+    b2lz4f_prefs d; if (!prefs) { b2lz4f_prefs_init(&d); prefs = &d; }
+    const size_t bound = b2lz4f_compress_frame_bound(n, prefs);
+    if (cap < bound) return B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL;   // src/lz4f.zig:363-366
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    size_t bs;
+    const int level = prefs->compression_level;
+    size_t chunk_blocks;
+    if (block_size_of(prefs->block_size_id, bs) && (level <= 0 || b2_hc_supported(level)) && pipeline_applies(n, bs, &chunk_blocks))
+        return compress_frame_pipelined(c, (const uint8_t*)src, n, (uint8_t*)dst, cap, prefs, bs, chunk_blocks, out);
+    return compress_frame_simple(c, src, n, dst, bound, prefs, out);
+}
+
+int b2lz4f_decompress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out) {
+    if (!c || !out) return B2LZ4F_ERR_PARAMETER_NULL;
+    *out = 0;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    if (n > (1u << 20) && src && dst) {
+        int rc = B2LZ4_OK;
+        if (decompress_frame_pipelined(c, (const uint8_t*)src, n, (uint8_t*)dst, cap, out, &rc)) return rc;
+        *out = 0;
+    }
+    return decompress_frame_simple(c, src, n, dst, cap, out);
 }
 
 int b2lz4f_compress_frame(const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs, size_t* out) {
