@@ -230,16 +230,96 @@ __device__ void compress_block_general(const uint8_t* __restrict__ src, uint32_t
 // acceleration == 1 (compressDefault, every frame block): the lean path.
 //
 // With step == 1 the reference's iterations visit q, q+1, q+2, ... (p_j = q + j for the first
-// 65 iterations), and the position e = q - 1 is the one put() after the previous match (:438-442).  So
-// the first window of a search is simply p = e + lane: lane 0 only inserts (never matches), lanes 1..31
-// are iterations 1..31.  anchor == e, hence the literal run of a match found by lane L is L bytes long
-// and its bytes are the low bytes of the lanes' own 4-byte reads.
-//
-// Intra-window put() order without MATCH.ANY: every active lane writes its position into its bucket
-// and reads it back.  If every lane reads its own value the 32 buckets are distinct (88 % of windows):
-// the table values read before the writes are the candidates, lanes up to the match keep their write
-// (= their put()), later lanes restore what they read.  Otherwise everything is restored and the
-// general resolution (__match_any_sync) runs.
+// 65 iterations), and the position e = q - 1 is the one put() after the previous match (:438-442).  A
+// window is therefore the 32 consecutive positions p = e + lane.  One window costs two dependent memory
+// round trips (the input words, then the bytes at the table candidates), so it is made to yield every
+// sequence that starts inside it, not just the first:
+//   * every lane reads its word, its bucket (`old`, the table before this window) and verifies `old`
+//     against its word (range test :345-347 + 4-byte compare :348) — once;
+//   * __match_any_sync groups the lanes by bucket.  While the window is walked, V is the set of lanes
+//     the reference really visits (probed or put()); a lane's candidate is the nearest earlier lane of
+//     its group that is in V (what the table would hold at that moment), else `old`;
+//   * the walk: lane `lo` is the last put() position, lanes lo+1.. are iterations 1.. of the next search
+//     (iterations 1 and 2 never take the exit at :335, later ones need p < lim); the first valid lane L
+//     is the match, its literals are the low bytes of lanes lo..L-1, the match end becomes the new `lo`
+//     and the lanes in between are never visited;
+//   * at the end each bucket gets the position of its last visited lane (later put() wins), or `old`
+//     if none of its lanes was visited.
+// A search that reaches lane 31 without a match continues in the general schedule (iteration 32 - lo
+// onwards, where the step grows).
+template <typename TableT>
+__device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cap,
+                                              uint32_t& op, uint32_t anchor, uint32_t LL, uint32_t ml, uint32_t offset,
+                                              bool lit_in_lanes, uint32_t litb, uint32_t lane) {
+    if (LL < RUN_MASK && ml < ML_MASK) {
+        // short form: token | literals | offset = LL + 3 <= 17 bytes, one byte per lane
+        const uint32_t seq_end = op + LL + 3;
+        if (seq_end > cap) return false;                         // monotone in op: see DESIGN.md
+        uint32_t bv = (LL << 4) | ml;
+        if (lane >= 1 && lane <= LL) bv = lit_in_lanes ? litb : (uint32_t)__ldg(src + anchor + lane - 1);
+        else if (lane == LL + 1) bv = offset;
+        else if (lane == LL + 2) bv = offset >> 8;
+        if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
+        op = seq_end;
+    } else {
+        const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+        const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+        const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+        if (seq_end > cap) return false;
+        uint8_t* o = dst + op;
+        if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
+        write_len_ext(o + 1, LL, nll, lane);
+        warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+        uint8_t* o2 = o + 1 + nll + LL;
+        if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
+        write_len_ext(o2 + 2, ml, nml, lane);
+        op = seq_end;
+    }
+    return true;
+}
+
+// match length beyond MINMATCH, :401-413 (limit n - 5)
+__device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src, uint32_t mpos, uint32_t mcand, uint32_t mlimit,
+                                                 uint32_t lane) {
+    uint32_t a = mpos + MINMATCH, b = mcand + MINMATCH, ml = 0;
+    uint32_t cnt = 4;   // first 16 bytes on four lanes; most matches end here
+    if (lane < 4) {
+        const uint32_t al = a + 4 * lane;
+        const uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+        cnt = 0;
+        if (nb) {
+            const uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+            const uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+            cnt = mm < nb ? mm : nb;
+        }
+    }
+    const uint32_t stopm = __ballot_sync(FULL, cnt < 4);
+    if (stopm) {
+        const uint32_t f = (uint32_t)__ffs(stopm) - 1;
+        return 4 * f + __shfl_sync(FULL, cnt, f);
+    }
+    ml = 16; a += 16; b += 16;
+    for (;;) {
+        uint32_t al = a + 4 * lane;
+        uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
+        uint32_t c2 = 0;
+        if (nb) {
+            uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
+            uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+            c2 = mm < nb ? mm : nb;
+        }
+        uint32_t sm = __ballot_sync(FULL, c2 < 4);
+        if (sm) {
+            uint32_t f = (uint32_t)__ffs(sm) - 1;
+            return ml + 4 * f + __shfl_sync(FULL, c2, f);
+        }
+        ml += 128; a += 128; b += 128;
+    }
+}
+
+// lanes a..b inclusive (a <= b <= 31)
+__device__ __forceinline__ uint32_t lane_range(uint32_t a, uint32_t b) { return ((2u << b) - 1u) & ~((1u << a) - 1u); }
+
 template <typename TableT>
 __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
                                   TableT* table, uint32_t lane, uint32_t& olen, int& st) {
@@ -261,167 +341,118 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
         const uint32_t lim = n - MFLIMIT;         // mflimitPlusOne, :313
         const uint32_t mlimit = n - LASTLITERALS;  // matchLimit, :314
         const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
-        uint32_t e = 0;  // position put() before the search starts at e + 1 (0: nothing, table value 0 == empty)
+        uint32_t e = 0;  // last put() position; the search starts at e + 1 (0: nothing put, table value 0 == empty)
 
         while (e + 1 < lim) {                                    // :320 with ip == e + 1
             if (lane == 0 && e + 512 < n) prefetch_l1(src + e + 512);
-            uint32_t mpos = 0, mcand = 0, LL = 0;
-            uint32_t litb = 0;      // short-form literal byte of this lane (window 0 only)
-            bool found = false, win0 = false;
-            {   // ---------------- window 0: p = e + lane ----------------
-                const uint32_t room = lim - e - 1;                       // lim - q >= 1
-                const uint32_t A = (room < 2 ? 2u : room) + 1;           // active lanes (iterations 1, 2 never exit)
-                const bool active = lane < A;
-                const uint32_t p = e + lane;
-                uint32_t v = 0, h = 0, old = 0;
-                if (active) { v = ld_u32x(src + p); h = hash4(v); old = table[h]; }
-                __syncwarp();
-                if (active) table[h] = (TableT)p;
-                __syncwarp();
-                bool clash = false;
-                if (active) clash = table[h] != (TableT)p;
-                const uint32_t cm = __ballot_sync(FULL, clash);
-                uint32_t cand = old;
-                uint32_t peers = 0;
-                if (cm) {                                                // rare: shared buckets inside the window
-                    if (active) table[h] = (TableT)old;
-                    peers = __match_any_sync(FULL, active ? h : (0x80000000u | lane));
-                    const uint32_t prev = peers & lt;
-                    const int sl = prev ? 31 - __clz(prev) : (int)lane;
-                    const uint32_t pp = __shfl_sync(FULL, p, sl);
-                    if (prev) cand = pp;
-                }
-                bool valid = active && lane > 0 && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;  // :345-347
-                if (valid) {
-                    const uint8_t* cp = src + cand;
-                    if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && cand + 19 < n) touch_sector(cp + 19);
-                    valid = (ld_u32x(cp) == v);                          // :348
-                }
-                const uint32_t vm = __ballot_sync(FULL, valid);
-                const uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
-                if (cm) {
-                    const uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
-                    const bool commit = active && lane <= L && ((peers & gt & le) == 0);
-                    __syncwarp();
-                    if (commit) table[h] = (TableT)p;
-                } else if (active && lane > L) {
-                    table[h] = (TableT)old;                              // iterations after the match never ran
-                }
-                __syncwarp();
-                if (vm) {
-                    found = true; win0 = true;
-                    mpos = e + L; LL = L;
-                    mcand = __shfl_sync(FULL, cand, L);
-                    litb = __shfl_up_sync(FULL, v, 1) & 0xFFu;           // lane i (1..LL) holds src[e + i - 1]
-                } else if (A < 32) {
-                    break;                                               // -> finishCompression, :335-338
-                }
+            // ---------------- window: p = base + lane ----------------
+            const uint32_t base = e;
+            const uint32_t p = base + lane;
+            const bool inwin = p <= lim;                         // positions the walk may touch (p + 3 <= n - 9)
+            uint32_t v = 0, h = 0x80000000u | lane, old = 0;
+            if (inwin) { v = ld_u32x(src + p); h = hash4(v); old = table[h]; }
+            const uint32_t peers = __match_any_sync(FULL, h);
+            bool vold = inwin && old > 0 && old + MAX_DISTANCE >= p;     // :345-347 (old < e <= p always)
+            if (vold) {
+                const uint8_t* cp = src + old;
+                if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && old + 19 < n) touch_sector(cp + 19);
+                vold = (ld_u32x(cp) == v);                               // :348
             }
-            if (!found) {
-                // ---------------- later windows (no match within 31 bytes): general schedule, a0 == 1 ----------------
-                const uint32_t q = e + 1;
-                uint32_t j0 = 31;
+            uint32_t lo = 0, V = 1u;            // lane `lo`: last put(); V: lanes the reference has visited
+            bool finish = false, more = false;  // finish: the block's search loop is over; more: search continues past lane 31
+            for (;;) {
+                // lanes lo+1.. are iterations 1.. of the search that starts at e + lo + 1 (< lim)
+                const bool elig = inwin && lane > lo && (p < lim || lane == lo + 2);
+                // candidate: nearest earlier lane of the same bucket that has been visited when this lane is probed
+                const uint32_t seen = V | ~((2u << lo) - 1u);            // visited so far + every lane after lo (probed before me)
+                const uint32_t pv = peers & lt & seen;
+                const int pl = pv ? 31 - __clz(pv) : (int)lane;
+                const uint32_t pvv = __shfl_sync(FULL, v, pl);
+                const bool valid = elig && (pv ? (pvv == v && base + pl > 0) : vold);
+                const uint32_t em = __ballot_sync(FULL, elig);           // a prefix range lo+1..hiE (may be empty)
+                const uint32_t m = __ballot_sync(FULL, valid);
+                if (m == 0) {
+                    V |= em;
+                    if (em & 0x80000000u) more = true; else finish = true;   // ran off the window / hit the exit at :335
+                    break;
+                }
+                const uint32_t L = (uint32_t)__ffs(m) - 1;
+                V |= lane_range(lo + 1, L);
+                const uint32_t cpl = __shfl_sync(FULL, (uint32_t)pl, L);
+                const uint32_t cpv = __shfl_sync(FULL, pv, L);
+                const uint32_t cold = __shfl_sync(FULL, old, L);
+                const uint32_t mpos = base + L;
+                const uint32_t mcand = cpv ? base + cpl : cold;
+                const uint32_t LL = L - lo;                              // anchor == e + lo
+                const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
+                const uint32_t litb = __shfl_sync(FULL, v, lo + lane - 1) & 0xFFu;   // lane t (1..LL): src[anchor + t - 1]
+                if (!emit_sequence<TableT>(src, dst, cap, op, base + lo, LL, ml, mpos - mcand, true, litb, lane)) {
+                    st = ST_OUTPUT_TOO_SMALL;
+                    return;
+                }
+                const uint32_t mend = mpos + MINMATCH + ml;
+                anchor = mend;                                           // :435
+                if (mend - base >= 31 || mend >= lim) {                  // next put() opens the next window, or there is none (:438)
+                    e = mend;
+                    break;
+                }
+                lo = mend - base;                                        // put(mend), :440
+                V |= 1u << lo;
+                if (mend + 1 >= lim) { finish = true; break; }           // :320
+            }
+            // ---------------- table after the window: last visited lane of every bucket, else unchanged ----------------
+            {
+                const uint32_t vg = peers & V;
+                const uint32_t wl = vg ? 31u - (uint32_t)__clz(vg) : 0u;
+                const uint32_t val = vg ? base + wl : old;
+                if (inwin && (peers & lt) == 0) table[h] = (TableT)val;
+            }
+            __syncwarp();
+            if (finish) break;
+            if (more) {
+                // ---------------- later windows of the same search: general schedule (a0 == 1), iteration 32 - lo onwards ----------------
+                const uint32_t q = base + lo + 1;
+                uint32_t j0 = 31 - lo;
+                uint32_t mpos = 0, mcand = 0;
+                bool found = false;
                 for (;;) {
                     uint32_t j = j0 + lane;
-                    uint32_t x = j + 63, s = x >> 6;                 // j >= 2: reference iteration k = j + 64, x = a0 + k - 2
-                    uint32_t p = q + 1 + step_prefix(x);             // step_prefix(1) == 0
-                    bool can = (p + s <= lim);                       // :335
+                    uint32_t pj, s;
+                    if (j < 2) { pj = q + j; s = j == 0 ? 1u : 0u; }     // iterations 1 and 2 (only when lo == 31, 30)
+                    else { uint32_t x = j + 63; s = x >> 6; pj = q + 1 + step_prefix(x); }
+                    bool can = (pj + s <= lim);                      // :335
                     uint32_t em = __ballot_sync(FULL, !can);
                     uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;
                     bool active = lane < E;
-                    uint32_t v = 0, h = 0x80000000u | lane, cand = 0;
-                    if (active) { v = ld_u32x(src + p); h = hash4(v); cand = table[h]; }
-                    uint32_t peers = __match_any_sync(FULL, h);
-                    uint32_t prev = peers & lt;
+                    uint32_t v2 = 0, h2 = 0x80000000u | lane, cand = 0;
+                    if (active) { v2 = ld_u32x(src + pj); h2 = hash4(v2); cand = table[h2]; }
+                    uint32_t peers2 = __match_any_sync(FULL, h2);
+                    uint32_t prev = peers2 & lt;
                     int sl = prev ? 31 - __clz(prev) : (int)lane;
-                    uint32_t pp = __shfl_sync(FULL, p, sl);
+                    uint32_t pp = __shfl_sync(FULL, pj, sl);
                     if (prev) cand = pp;
-                    bool valid = active && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;
-                    if (valid) valid = (ld_u32x(src + cand) == v);
+                    bool valid = active && cand > 0 && cand < pj && cand + MAX_DISTANCE >= pj;
+                    if (valid) valid = (ld_u32x(src + cand) == v2);
                     uint32_t vm = __ballot_sync(FULL, valid);
                     uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
                     uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
-                    bool commit = active && lane <= L && ((peers & gt & le) == 0);
+                    bool commit = active && lane <= L && ((peers2 & gt & le) == 0);
                     __syncwarp();
-                    if (commit) table[h] = (TableT)p;
+                    if (commit) table[h2] = (TableT)pj;
                     __syncwarp();
-                    if (vm) { mpos = __shfl_sync(FULL, p, L); mcand = __shfl_sync(FULL, cand, L); found = true; break; }
+                    if (vm) { mpos = __shfl_sync(FULL, pj, L); mcand = __shfl_sync(FULL, cand, L); found = true; break; }
                     if (E < 32) break;
                     j0 += 32;
                 }
                 if (!found) break;
-                LL = mpos - anchor;                                      // :360
-            }
-
-            // ---------------- match extension, :401-413 ----------------
-            const uint32_t offset = mpos - mcand;                        // :395
-            uint32_t a = mpos + MINMATCH, b = mcand + MINMATCH, ml = 0;
-            {   // first 16 bytes on four lanes; most matches end here
-                uint32_t cnt = 4;
-                if (lane < 4) {
-                    const uint32_t al = a + 4 * lane;
-                    const uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
-                    cnt = 0;
-                    if (nb) {
-                        const uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
-                        const uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                        cnt = mm < nb ? mm : nb;
-                    }
+                const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
+                if (!emit_sequence<TableT>(src, dst, cap, op, anchor, mpos - anchor, ml, mpos - mcand, false, 0, lane)) {
+                    st = ST_OUTPUT_TOO_SMALL;
+                    return;
                 }
-                const uint32_t stopm = __ballot_sync(FULL, cnt < 4);
-                if (stopm) {
-                    const uint32_t f = (uint32_t)__ffs(stopm) - 1;
-                    ml = 4 * f + __shfl_sync(FULL, cnt, f);
-                } else {
-                    ml = 16; a += 16; b += 16;
-                    for (;;) {
-                        uint32_t al = a + 4 * lane;
-                        uint32_t nb = al >= mlimit ? 0u : (mlimit - al >= 4 ? 4u : mlimit - al);
-                        uint32_t c2 = 0;
-                        if (nb) {
-                            uint32_t x = ld_u32x(src + al) ^ ld_u32x(src + b + 4 * lane);
-                            uint32_t mm = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                            c2 = mm < nb ? mm : nb;
-                        }
-                        uint32_t sm = __ballot_sync(FULL, c2 < 4);
-                        if (sm) {
-                            uint32_t f = (uint32_t)__ffs(sm) - 1;
-                            ml += 4 * f + __shfl_sync(FULL, c2, f);
-                            break;
-                        }
-                        ml += 128; a += 128; b += 128;
-                    }
-                }
+                anchor = mpos + MINMATCH + ml;
+                e = anchor;
             }
-            const uint32_t mend = mpos + MINMATCH + ml;
-
-            // ---------------- emit sequence, :362-432 ----------------
-            if (LL < RUN_MASK && ml < ML_MASK) {
-                // short form: token | literals | offset = LL + 3 <= 17 bytes, one byte per lane
-                const uint32_t seq_end = op + LL + 3;
-                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }  // monotone in op: see DESIGN.md
-                uint32_t bv = (LL << 4) | ml;
-                if (lane >= 1 && lane <= LL) bv = win0 ? litb : (uint32_t)__ldg(src + anchor + lane - 1);
-                else if (lane == LL + 1) bv = offset;
-                else if (lane == LL + 2) bv = offset >> 8;
-                if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
-                op = seq_end;
-            } else {
-                const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
-                const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
-                const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
-                if (seq_end > cap) { st = ST_OUTPUT_TOO_SMALL; return; }
-                uint8_t* o = dst + op;
-                if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
-                write_len_ext(o + 1, LL, nll, lane);
-                warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
-                uint8_t* o2 = o + 1 + nll + LL;
-                if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
-                write_len_ext(o2 + 2, ml, nml, lane);
-                op = seq_end;
-            }
-            anchor = mend;                                       // :435
-            e = mend;                                            // put(e) is lane 0 of the next window (:438-442)
         }
     }
 
