@@ -247,6 +247,26 @@ __device__ void compress_block_general(const uint8_t* __restrict__ src, uint32_t
 //     if none of its lanes was visited.
 // A search that reaches lane 31 without a match continues in the general schedule (iteration 32 - lo
 // onwards, where the step grows).
+// long form of a sequence (length-extension bytes and/or long literal run), :362-432
+__device__ __noinline__ bool emit_sequence_long(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cap,
+                                                uint32_t* op_io, uint32_t anchor, uint32_t LL, uint32_t ml, uint32_t offset,
+                                                uint32_t lane) {
+    const uint32_t op = *op_io;
+    const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+    const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+    const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+    if (seq_end > cap) return false;
+    uint8_t* o = dst + op;
+    if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
+    write_len_ext(o + 1, LL, nll, lane);
+    warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
+    uint8_t* o2 = o + 1 + nll + LL;
+    if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
+    write_len_ext(o2 + 2, ml, nml, lane);
+    *op_io = seq_end;
+    return true;
+}
+
 template <typename TableT>
 __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cap,
                                               uint32_t& op, uint32_t anchor, uint32_t LL, uint32_t ml, uint32_t offset,
@@ -262,26 +282,15 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
         if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
         op = seq_end;
     } else {
-        const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
-        const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
-        const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
-        if (seq_end > cap) return false;
-        uint8_t* o = dst + op;
-        if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
-        write_len_ext(o + 1, LL, nll, lane);
-        warp_copy<true>(o + 1 + nll, src + anchor, LL, lane);
-        uint8_t* o2 = o + 1 + nll + LL;
-        if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
-        write_len_ext(o2 + 2, ml, nml, lane);
-        op = seq_end;
+        return emit_sequence_long(src, dst, cap, &op, anchor, LL, ml, offset, lane);
     }
     return true;
 }
 
-// match length beyond MINMATCH, :401-413 (limit n - 5)
-__device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src, uint32_t mpos, uint32_t mcand, uint32_t mlimit,
+// number of equal bytes of src[a..] and src[b..] (b < a), stopping at mlimit = n - 5 — the loop at :401-413
+__device__ __noinline__ uint32_t extend_bytes(const uint8_t* __restrict__ src, uint32_t a, uint32_t b, uint32_t mlimit,
                                                  uint32_t lane) {
-    uint32_t a = mpos + MINMATCH, b = mcand + MINMATCH, ml = 0;
+    uint32_t ml = 0;
     uint32_t cnt = 4;   // first 16 bytes on four lanes; most matches end here
     if (lane < 4) {
         const uint32_t al = a + 4 * lane;
@@ -318,6 +327,11 @@ __device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src
 }
 
 // lanes a..b inclusive (a <= b <= 31)
+__device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src, uint32_t mpos, uint32_t mcand, uint32_t mlimit,
+                                                 uint32_t lane) {
+    return extend_bytes(src, mpos + MINMATCH, mcand + MINMATCH, mlimit, lane);
+}
+
 __device__ __forceinline__ uint32_t lane_range(uint32_t a, uint32_t b) { return ((2u << b) - 1u) & ~((1u << a) - 1u); }
 
 template <typename TableT>
@@ -353,10 +367,40 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             if (inwin) { v = ld_u32x(src + p); h = hash4(v); old = table[h]; }
             const uint32_t peers = __match_any_sync(FULL, h);
             bool vold = inwin && old > 0 && old + MAX_DISTANCE >= p;     // :345-347 (old < e <= p always)
+            // One 16-byte read at the candidate serves the 4-byte compare (:348) and stages the next
+            // 5..12 bytes of the match (m1..m3, nmb of them valid) for the extension (:401-413).
+            uint32_t m1 = 0, m2 = 0, m3 = 0, nmb = 0;
             if (vold) {
-                const uint8_t* cp = src + old;
-                if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && old + 19 < n) touch_sector(cp + 19);
-                vold = (ld_u32x(cp) == v);                               // :348
+                const uintptr_t ca = reinterpret_cast<uintptr_t>(src + old);
+                const uint2* c8 = reinterpret_cast<const uint2*>(ca & ~uintptr_t(7));
+                const uint2 A = __ldg(c8);
+                const uint32_t c = (uint32_t)(ca & 7);
+                // second half only if it holds input bytes (old + 8 - c < n always: old < p <= n - 12)
+                const uint2 B = __ldg(c8 + 1);
+                const uint32_t sh = (c & 3) * 8;
+                const bool hiw = c >= 4;
+                const uint32_t w0 = hiw ? A.y : A.x, w1 = hiw ? B.x : A.y, w2 = hiw ? B.y : B.x, w3 = hiw ? 0u : B.y;
+                vold = (__funnelshift_r(w0, w1, sh) == v);               // :348
+                m1 = __funnelshift_r(w1, w2, sh);
+                m2 = __funnelshift_r(w2, w3, sh);
+                m3 = __funnelshift_r(w3, 0u, sh);
+                nmb = 12 - c;
+            }
+            // Every lane extends its own (table) match as far as the staged bytes reach: the forward words
+            // are the reads of lanes +4, +8, +12.  mlpk = length | "bytes exhausted, continue from memory" << 8.
+            uint32_t mlpk;
+            {
+                const uint32_t F1 = __shfl_down_sync(FULL, v, 4), F2 = __shfl_down_sync(FULL, v, 8), F3 = __shfl_down_sync(FULL, v, 12);
+                uint32_t nfw = (31 - lane) >> 2;                         // forward words held by lanes +4, +8, +12 ...
+                const uint32_t roomw = inwin ? (lim - p) >> 2 : 0u;      // ... that lie inside the window (position <= lim)
+                nfw = nfw < roomw ? nfw : roomw;
+                nfw = nfw < 3 ? nfw : 3;
+                const uint32_t navail = 4 * nfw < nmb ? 4 * nfw : nmb;
+                const uint32_t x1 = F1 ^ m1, x2 = F2 ^ m2, x3 = F3 ^ m3;
+                const uint32_t d = x1 ? (uint32_t)(__ffs(x1) - 1) >> 3
+                                      : 4 + (x2 ? (uint32_t)(__ffs(x2) - 1) >> 3 : 4 + (x3 ? (uint32_t)(__ffs(x3) - 1) >> 3 : 4u));
+                const bool more_bytes = d >= navail && p + MINMATCH + navail < mlimit;
+                mlpk = (d < navail ? d : navail) | (more_bytes ? 0x100u : 0u);
             }
             uint32_t lo = 0, V = 1u;            // lane `lo`: last put(); V: lanes the reference has visited
             bool finish = false, more = false;  // finish: the block's search loop is over; more: search continues past lane 31
@@ -378,13 +422,17 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 }
                 const uint32_t L = (uint32_t)__ffs(m) - 1;
                 V |= lane_range(lo + 1, L);
-                const uint32_t cpl = __shfl_sync(FULL, (uint32_t)pl, L);
-                const uint32_t cpv = __shfl_sync(FULL, pv, L);
-                const uint32_t cold = __shfl_sync(FULL, old, L);
                 const uint32_t mpos = base + L;
-                const uint32_t mcand = cpv ? base + cpl : cold;
-                const uint32_t LL = L - lo;                              // anchor == e + lo
-                const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
+                const uint32_t mcand = __shfl_sync(FULL, pv ? base + (uint32_t)pl : old, L);
+                const uint32_t LL = L - lo;                              // anchor == base + lo
+                uint32_t ml;
+                if (mcand < base) {                                      // table candidate: extension already measured
+                    const uint32_t pk = __shfl_sync(FULL, mlpk, L);
+                    ml = pk & 0xFFu;
+                    if (pk >> 8) ml += extend_bytes(src, mpos + MINMATCH + ml, mcand + MINMATCH + ml, mlimit, lane);
+                } else {                                                 // candidate inside the window (runs, short periods)
+                    ml = extend_bytes(src, mpos + MINMATCH, mcand + MINMATCH, mlimit, lane);
+                }
                 const uint32_t litb = __shfl_sync(FULL, v, lo + lane - 1) & 0xFFu;   // lane t (1..LL): src[anchor + t - 1]
                 if (!emit_sequence<TableT>(src, dst, cap, op, base + lo, LL, ml, mpos - mcand, true, litb, lane)) {
                     st = ST_OUTPUT_TOO_SMALL;
@@ -477,7 +525,7 @@ __device__ __forceinline__ void compress_block(const uint8_t* __restrict__ src, 
 }
 
 template <typename TableT>
-__global__ void __launch_bounds__(K1_THREADS) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
+__global__ void __launch_bounds__(96, 9) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                               int32_t* __restrict__ status, uint32_t nblocks,
                                                               uint32_t accel, uint32_t* ticket) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
