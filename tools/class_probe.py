@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--block-id", type=int, default=4)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--classes", default="text,binary,redundant,random,mixed")
 a = ap.parse_args()
 n = a.mib << 20
 ctx = z.Context(0)
@@ -21,6 +22,8 @@ host = torch.empty(n, dtype=torch.uint8).pin_memory()
 comp = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
 back = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
 for name, mode in (("text", 0), ("binary", 1), ("redundant", 2), ("random", 3), ("mixed", 4)):
+    if name not in a.classes.split(","):
+        continue
     datagen.fill_ptr(host.data_ptr(), n, mode=mode, span=65536)
     src = host.to("cuda")
     best_c = best_d = best_i = 1e9

@@ -66,6 +66,15 @@ struct HostResults {
 
 }  // namespace b2
 
+// Workspace of one in-flight chunk of the host-pointer pipeline (index 0 aliases the context's own buffers).
+struct b2_ws_ref {
+    b2::DevBuf *slots, *csize, *status, *sums, *rec_off;
+    uint32_t* ticket;
+    b2::FrameTotals* totals;
+    b2::DecodeSummary* summary;
+    cudaStream_t stream;
+};
+
 struct b2lz4_ctx {
     int device = 0;
     int num_sms = 148;
@@ -74,14 +83,17 @@ struct b2lz4_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pointer pipeline
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t[8] = {};
-    cudaEvent_t ev_pipe[8] = {};
+    cudaEvent_t ev_pipe[12] = {};
     std::recursive_mutex mu;
     bool timing = false;
     float phase_ms[5] = {0, 0, 0, 0, 0};
     // workspace
     b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, hc_work;
     b2::DevBuf idx_tiles, idx_pos, idx_jump;   // parallel frame index scratch
-    b2::DevBuf stage_in[2], stage_out[2], stage_aux;
+    b2::DevBuf stage_in[3], stage_out[3], stage_aux;
+    // two more chunk workspaces + compute streams for the host-pointer pipeline (three chunks in flight)
+    b2::DevBuf x_slots[2], x_csize[2], x_status[2], x_sums[2], x_rec_off[2], x_small[2];
+    cudaStream_t x_stream[2] = {nullptr, nullptr};
     b2::PinBuf results, pin_aux;
     // layout of `small` (device): ticket u32 @0, FrameTotals @64, WalkResult @128, DecodeSummary @192,
     // content_sum u32 @256, XxhState @320, index node count u64 @512
@@ -94,6 +106,13 @@ struct b2lz4_ctx {
     uint64_t* d_idx_nodes() const { return reinterpret_cast<uint64_t*>(small.as<uint8_t>() + 512); }
     b2::HostResults* h() const { return results.as<b2::HostResults>(); }
     size_t workspace_bytes() const;
+    b2_ws_ref ws(int i) {
+        if (i == 0) return b2_ws_ref{&slots, &csize, &status, &sums, &rec_off, d_ticket(), d_totals(), d_summary(), stream};
+        uint8_t* sm = x_small[i - 1].as<uint8_t>();
+        return b2_ws_ref{&x_slots[i - 1], &x_csize[i - 1], &x_status[i - 1], &x_sums[i - 1], &x_rec_off[i - 1],
+                         reinterpret_cast<uint32_t*>(sm), reinterpret_cast<b2::FrameTotals*>(sm + 64),
+                         reinterpret_cast<b2::DecodeSummary*>(sm + 192), x_stream[i - 1]};
+    }
 };
 
 // internal entry points shared between translation units
@@ -101,6 +120,6 @@ int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, siz
                          size_t* out, cudaStream_t s, bool body_only);
 int b2_decompress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, size_t* out, cudaStream_t s);
 int b2_default_ctx(b2lz4_ctx** out);
-int b2_enqueue_body(b2lz4_ctx* c, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body, cudaStream_t s,
-                    bool timing);
+int b2_enqueue_body(b2lz4_ctx* c, const b2_ws_ref& w, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body,
+                    cudaStream_t s, bool timing);
 int b2_hc_supported(int level);

@@ -70,7 +70,8 @@ int b2_hc_supported(int level) { return hc_nb_searches(level) >= 0 ? 1 : 0; }
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
                out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap;
-    for (int i = 0; i < 2; i++) t += stage_in[i].cap + stage_out[i].cap;
+    for (int i = 0; i < 3; i++) t += stage_in[i].cap + stage_out[i].cap;
+    for (int i = 0; i < 2; i++) t += x_slots[i].cap + x_csize[i].cap + x_status[i].cap + x_sums[i].cap + x_rec_off[i].cap + x_small[i].cap;
     return t;
 }
 
@@ -117,6 +118,11 @@ int b2lz4_ctx_create(int device, b2lz4_ctx** out) {
     B2_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     B2_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     B2_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        B2_CUDA(cudaStreamCreateWithFlags(&c->x_stream[i], cudaStreamNonBlocking));
+        B2_CUDA(c->x_small[i].ensure(1024));
+        B2_CUDA(cudaMemset(c->x_small[i].p, 0, 1024));
+    }
     B2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     B2_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& e : c->ev_t) B2_CUDA(cudaEventCreate(&e));
@@ -134,8 +140,10 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->slots, &c->csize, &c->status, &c->sums, &c->rec_off, &c->small, &c->walk_off, &c->walk_hdr,
-                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1],
-                      &c->stage_aux};
+                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
+                      &c->stage_out[0], &c->stage_out[1], &c->stage_out[2], &c->stage_aux,
+                      &c->x_slots[0], &c->x_slots[1], &c->x_csize[0], &c->x_csize[1], &c->x_status[0], &c->x_status[1],
+                      &c->x_sums[0], &c->x_sums[1], &c->x_rec_off[0], &c->x_rec_off[1], &c->x_small[0], &c->x_small[1]};
     for (auto* b : bufs) b->release();
     c->results.release();
     c->pin_aux.release();
@@ -147,6 +155,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     if (c->side) cudaStreamDestroy(c->side);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
+    for (auto& xs : c->x_stream) if (xs) cudaStreamDestroy(xs);
     delete c;
 }
 int b2lz4_ctx_device(const b2lz4_ctx* c) { return c ? c->device : -1; }
@@ -311,23 +320,23 @@ static int ensure_hc_work(b2lz4_ctx* c, cudaStream_t s) {
 }
 
 // Runs the block codec for the blocks of [src, src+n) into the context's slots.  level 0 = fast.
-static int encode_blocks_to_slots(b2lz4_ctx* c, const void* src, size_t n, size_t bs, int level, uint32_t nb,
-                                  cudaStream_t s) {
+static int encode_blocks_to_slots(b2lz4_ctx* c, const b2_ws_ref& w, const void* src, size_t n, size_t bs, int level,
+                                  uint32_t nb, cudaStream_t s) {
     const size_t stride = slot_stride_for(bs);
-    B2_CUDA(c->slots.ensure((size_t)nb * stride));
-    B2_CUDA(c->csize.ensure((size_t)nb * 4));
-    B2_CUDA(c->status.ensure((size_t)nb * 4));
+    B2_CUDA(w.slots->ensure((size_t)nb * stride));
+    B2_CUDA(w.csize->ensure((size_t)nb * 4));
+    B2_CUDA(w.status->ensure((size_t)nb * 4));
     BlockSet in = regular_in(src, bs, n);
-    OutSet out = regular_out(c->slots.p, stride, (uint64_t)nb * stride, (uint32_t)compress_bound(bs));
+    OutSet out = regular_out(w.slots->p, stride, (uint64_t)nb * stride, (uint32_t)compress_bound(bs));
     if (level > 0) {
         int nbs = hc_nb_searches(level);
         if (nbs < 0) return B2LZ4_ERR_UNSUPPORTED_LEVEL;
         { int rc = ensure_hc_work(c, s); if (rc) return rc; }
-        B2_CUDA(launch_compress_hc(in, out, c->csize.as<uint32_t>(), c->status.as<int32_t>(), nb, nbs,
-                                   c->hc_work.as<uint8_t>(), c->d_ticket(), c->num_sms, s));
+        B2_CUDA(launch_compress_hc(in, out, w.csize->as<uint32_t>(), w.status->as<int32_t>(), nb, nbs,
+                                   c->hc_work.as<uint8_t>(), w.ticket, c->num_sms, s));
     } else {
-        B2_CUDA(launch_compress_fast(in, out, c->csize.as<uint32_t>(), c->status.as<int32_t>(), nb, (uint32_t)bs, 1,
-                                     c->d_ticket(), c->num_sms, s));
+        B2_CUDA(launch_compress_fast(in, out, w.csize->as<uint32_t>(), w.status->as<int32_t>(), nb, (uint32_t)bs, 1,
+                                     w.ticket, c->num_sms, s));
     }
     return B2LZ4_OK;
 }
@@ -335,23 +344,23 @@ static int encode_blocks_to_slots(b2lz4_ctx* c, const void* src, size_t n, size_
 }  // namespace
 // Enqueues block codec -> block checksums -> record scan -> assembly for the blocks of [src, src+n) (device)
 // into `body` (device) on stream s.  Nothing is synchronised; the totals end up in c->d_totals().
-int b2_enqueue_body(b2lz4_ctx* c, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body, cudaStream_t s,
-                    bool timing) {
+int b2_enqueue_body(b2lz4_ctx* c, const b2_ws_ref& w, const void* src, size_t n, size_t bs, int level, bool bc, uint8_t* body,
+                    cudaStream_t s, bool timing) {
     const uint32_t nb = (uint32_t)((n + bs - 1) / bs);
     Timer T{c, s, timing};
-    if (nb) { int rc = encode_blocks_to_slots(c, src, n, bs, level, nb, s); if (rc) return rc; }
-    else { B2_CUDA(c->csize.ensure(4)); B2_CUDA(c->status.ensure(4)); }
+    if (nb) { int rc = encode_blocks_to_slots(c, w, src, n, bs, level, nb, s); if (rc) return rc; }
+    else { B2_CUDA(w.csize->ensure(4)); B2_CUDA(w.status->ensure(4)); }
     T.mark(1);
     const size_t stride = slot_stride_for(bs);
-    BlockSet slots = regular_in(c->slots.p, stride, (uint64_t)nb * stride);
+    BlockSet slots = regular_in(w.slots->p, stride, (uint64_t)nb * stride);
     BlockSet raw = regular_in(src, bs, n);
-    B2_CUDA(c->sums.ensure((size_t)nb * 4 + 4));
-    if (bc && nb) B2_CUDA(launch_xxh32_stored(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), nb, s));
+    B2_CUDA(w.sums->ensure((size_t)nb * 4 + 4));
+    if (bc && nb) B2_CUDA(launch_xxh32_stored(slots, raw, w.csize->as<uint32_t>(), w.sums->as<uint32_t>(), nb, s));
     T.mark(2);
-    B2_CUDA(c->rec_off.ensure(((size_t)nb + 1) * 8));
-    B2_CUDA(launch_scan_records(c->csize.as<uint32_t>(), c->status.as<int32_t>(), nb, bs, n, bc ? 1 : 0,
-                                c->rec_off.as<uint64_t>(), c->d_totals(), s));
-    if (nb) B2_CUDA(launch_assemble(slots, raw, c->csize.as<uint32_t>(), c->sums.as<uint32_t>(), c->rec_off.as<uint64_t>(),
+    B2_CUDA(w.rec_off->ensure(((size_t)nb + 1) * 8));
+    B2_CUDA(launch_scan_records(w.csize->as<uint32_t>(), w.status->as<int32_t>(), nb, bs, n, bc ? 1 : 0,
+                                w.rec_off->as<uint64_t>(), w.totals, s));
+    if (nb) B2_CUDA(launch_assemble(slots, raw, w.csize->as<uint32_t>(), w.sums->as<uint32_t>(), w.rec_off->as<uint64_t>(),
                                     body, nb, bc ? 1 : 0, c->num_sms, s));
     return B2LZ4_OK;
 }
@@ -401,7 +410,7 @@ int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, siz
         if (c->timing) cudaEventRecord(c->ev_t[6], c->side);
         B2_CUDA(cudaEventRecord(c->ev_join, c->side));
     }
-    { int rc = b2_enqueue_body(c, src, n, bs, level, bc, d8 + hsize, s, c->timing); if (rc) return rc; }
+    { int rc = b2_enqueue_body(c, c->ws(0), src, n, bs, level, bc, d8 + hsize, s, c->timing); if (rc) return rc; }
     if (!body_only) {
         if (cc) B2_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
         B2_CUDA(launch_finalize(d8, hsize, c->d_totals(), cc ? c->d_content_sum() : nullptr, s));

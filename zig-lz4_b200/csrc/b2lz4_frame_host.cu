@@ -91,7 +91,7 @@ static int decompress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void
 // chunk k-1.  Input and output are double-buffered on the device (2 x chunk), so the workspace no longer
 // grows with the frame.  PCIe moves N + C bytes each way per round trip; the kernels hide behind that.
 // A chunk must hold enough blocks to fill the GPU (one warp per block, ~4000 warps resident), so chunks
-// are sized in blocks: 4096 blocks, at most 256 MiB of raw data; frames whose block size leaves fewer
+// are sized in blocks: 2048 blocks (three chunks in flight keep the GPU full), at most 256 MiB of raw data; frames whose block size leaves fewer
 // than 1024 blocks per chunk (1 MiB / 4 MiB blocks) and frames shorter than three chunks take the
 // one-shot path.  B2_PIPE_BLOCKS overrides the block count (tests use it to pipeline small frames).
 constexpr size_t PIPE_MAX_CHUNK = 256u << 20;
@@ -99,7 +99,7 @@ static size_t pipe_blocks_for(size_t bs, bool* forced) {
     const char* e = getenv("B2_PIPE_BLOCKS");
     if (e && atol(e) > 0) { *forced = true; return (size_t)atol(e); }
     *forced = false;
-    size_t blocks = 4096;
+    size_t blocks = 2048;
     if (blocks * bs > PIPE_MAX_CHUNK) blocks = PIPE_MAX_CHUNK / bs;
     return blocks;
 }
@@ -116,6 +116,14 @@ static inline uint32_t rd32(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+constexpr int PIPE_DEPTH = 3;   // chunks in flight: staging buffers, workspaces and compute streams
+
+static void pipe_drain(b2lz4_ctx* c) {
+    cudaStreamSynchronize(c->stream);
+    for (auto xs : c->x_stream) cudaStreamSynchronize(xs);
+    cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side);
+}
+
 static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, uint8_t* dst, size_t cap,
                                     const b2lz4f_prefs* prefs, size_t bs, size_t chunk_blocks, size_t* out) {
     const bool bc = prefs->block_checksum == 1, cc = prefs->content_checksum == 1;
@@ -126,23 +134,27 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
     const size_t nchunks = (n + chunk - 1) / chunk;
     const size_t rec_bound = 4 + compress_bound(bs) + (bc ? 4 : 0);
     const size_t out_bound = (chunk / bs) * rec_bound;
-    for (int b = 0; b < 2; b++) {
+    // HC keeps its chain tables per resident warp in one shared buffer: its chunks run on one stream
+    const int nws = level > 0 ? 1 : PIPE_DEPTH;
+    for (int b = 0; b < PIPE_DEPTH; b++) {
         B2_CUDA(c->stage_in[b].ensure(chunk + 16));
         B2_CUDA(c->stage_out[b].ensure(out_bound + 16));
     }
-    cudaStream_t s = c->stream;
-    cudaEvent_t* ev_up = &c->ev_pipe[0];     // [2] chunk uploaded
-    cudaEvent_t* ev_done = &c->ev_pipe[2];   // [2] chunk computed (input buffer free, totals on the host)
-    cudaEvent_t* ev_down = &c->ev_pipe[4];   // [2] chunk downloaded (output buffer free)
-    cudaEvent_t* ev_cc = &c->ev_pipe[6];     // [2] content checksum consumed the chunk
+    cudaEvent_t* ev_up = &c->ev_pipe[0];     // [3] chunk uploaded
+    cudaEvent_t* ev_done = &c->ev_pipe[3];   // [3] chunk computed (input buffer free, totals on the host)
+    cudaEvent_t* ev_down = &c->ev_pipe[6];   // [3] chunk downloaded (output buffer free)
+    cudaEvent_t* ev_cc = &c->ev_pipe[9];     // [3] content checksum consumed the chunk
     if (cc) B2_CUDA(launch_xxh32_init(c->d_xxh(), 0, c->side));
     size_t pos = hsize;
     int err = B2LZ4_OK;
-    for (size_t k = 0; k <= nchunks; k++) {
+    const size_t lead = PIPE_DEPTH - 1;      // chunks enqueued ahead of the one being retired
+    for (size_t k = 0; k < nchunks + lead; k++) {
         if (k < nchunks) {                                   // ---- enqueue chunk k
-            const int b = (int)(k & 1);
+            const int b = (int)(k % PIPE_DEPTH);
+            const b2_ws_ref w = c->ws(nws == 1 ? 0 : b);
+            cudaStream_t s = w.stream;
             const size_t o = k * chunk, len = std::min(chunk, n - o);
-            if (k >= 2) {                                    // buffers of chunk k-2 must be free again
+            if (k >= (size_t)PIPE_DEPTH) {                   // buffers of chunk k - DEPTH must be free again
                 B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_done[b], 0));
                 if (cc) B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_cc[b], 0));
                 B2_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
@@ -155,15 +167,16 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
                 B2_CUDA(launch_xxh32_update(c->d_xxh(), c->stage_in[b].as<uint8_t>(), len, c->side));
                 B2_CUDA(cudaEventRecord(ev_cc[b], c->side));
             }
-            int rc = b2_enqueue_body(c, c->stage_in[b].p, len, bs, level, bc, c->stage_out[b].as<uint8_t>(), s, false);
+            int rc = b2_enqueue_body(c, w, c->stage_in[b].p, len, bs, level, bc, c->stage_out[b].as<uint8_t>(), s, false);
             if (rc) { err = rc; break; }
-            B2_CUDA(cudaMemcpyAsync(&c->h()->pipe_totals[k & 3], c->d_totals(), sizeof(FrameTotals), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaMemcpyAsync(&c->h()->pipe_totals[k & 3], w.totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, s));
             B2_CUDA(cudaEventRecord(ev_done[b], s));
         }
-        if (k >= 1) {                                        // ---- retire chunk k-1: its size is known now
-            const int b = (int)((k - 1) & 1);
+        if (k >= lead) {                                     // ---- retire chunk k - lead: its size is known now
+            const size_t kk = k - lead;
+            const int b = (int)(kk % PIPE_DEPTH);
             B2_CUDA(cudaEventSynchronize(ev_done[b]));
-            const FrameTotals t = c->h()->pipe_totals[(k - 1) & 3];
+            const FrameTotals t = c->h()->pipe_totals[kk & 3];
             if (t.first_bad != 0xFFFFFFFFu) {                // mapCompressionError, src/lz4f.zig:144-149
                 err = t.bad_status == B2LZ4_ERR_OUTPUT_TOO_SMALL ? B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL : B2LZ4F_ERR_GENERIC;
                 break;
@@ -173,7 +186,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
             pos += t.body_bytes;
         }
     }
-    if (err) { cudaStreamSynchronize(s); cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side); return err; }
+    if (err) { pipe_drain(c); return err; }
     if (cc) {
         B2_CUDA(launch_xxh32_final(c->d_xxh(), c->d_content_sum(), c->side));
         B2_CUDA(cudaMemcpyAsync(&c->h()->content_sum, c->d_content_sum(), 4, cudaMemcpyDeviceToHost, c->side));
@@ -191,8 +204,8 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
     return B2LZ4_OK;
 }
 
-// Returns 1 if the frame was decoded, 0 if the caller must take the one-shot path (anything unusual),
-// < 0 never; errors of the CUDA runtime are reported through *rc_out.
+// Returns 1 if the frame was decoded (or a CUDA error is reported through *rc_out), 0 if the caller must take
+// the one-shot path (anything unusual).
 static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out,
                                       int* rc_out) {
     *rc_out = B2LZ4_OK;
@@ -233,10 +246,9 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
         max_in = std::max(max_in, (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - (off[i0] - 4)));
         max_blocks = std::max(max_blocks, i1 - i0);
     }
-    cudaStream_t s = c->stream;
-    auto fail = [&](cudaError_t e, const char* what) { set_cuda_error(e, what); *rc_out = B2LZ4_ERR_CUDA; return 1; };
+    auto fail = [&](cudaError_t e, const char* what) { set_cuda_error(e, what); *rc_out = B2LZ4_ERR_CUDA; pipe_drain(c); return 1; };
 #define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(_e, #expr); } while (0)
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < PIPE_DEPTH; b++) {
         PIPE_CUDA(c->stage_in[b].ensure(max_in + 32));
         PIPE_CUDA(c->stage_out[b].ensure(max_blocks * bs + 16));
     }
@@ -251,28 +263,31 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
         const uint64_t lo = off[cfirst[k]] - 4;
         for (size_t i = cfirst[k]; i < cfirst[k + 1]; i++) rel[i] = off[i] - lo;
     }
-    PIPE_CUDA(cudaMemcpyAsync(c->walk_off.p, rel.data(), nb * 8, cudaMemcpyHostToDevice, s));
-    PIPE_CUDA(cudaMemcpyAsync(c->walk_hdr.p, hdr.data(), nb * 4, cudaMemcpyHostToDevice, s));
+    PIPE_CUDA(cudaMemcpyAsync(c->walk_off.p, rel.data(), nb * 8, cudaMemcpyHostToDevice, c->copy_in));
+    PIPE_CUDA(cudaMemcpyAsync(c->walk_hdr.p, hdr.data(), nb * 4, cudaMemcpyHostToDevice, c->copy_in));
     cudaEvent_t* ev_up = &c->ev_pipe[0];
-    cudaEvent_t* ev_done = &c->ev_pipe[2];
-    cudaEvent_t* ev_down = &c->ev_pipe[4];
-    cudaEvent_t* ev_cc = &c->ev_pipe[6];
+    cudaEvent_t* ev_done = &c->ev_pipe[3];
+    cudaEvent_t* ev_down = &c->ev_pipe[6];
+    cudaEvent_t* ev_cc = &c->ev_pipe[9];
     if (cc) PIPE_CUDA(launch_xxh32_init(c->d_xxh(), 0, c->side));
     bool unusual = false;
     size_t total = 0;
-    for (size_t k = 0; k <= nchunks && !unusual; k++) {
+    const size_t lead = PIPE_DEPTH - 1;
+    for (size_t k = 0; k < nchunks + lead && !unusual; k++) {
         if (k < nchunks) {
-            const int b = (int)(k & 1);
+            const int b = (int)(k % PIPE_DEPTH);
+            const b2_ws_ref w = c->ws(b);
+            cudaStream_t s = w.stream;
             const size_t i0 = cfirst[k], i1 = cfirst[k + 1], cnt = i1 - i0;
             const uint64_t lo = off[i0] - 4;
             const size_t in_len = (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - lo);
-            if (k >= 2) {
+            if (k >= (size_t)PIPE_DEPTH) {
                 PIPE_CUDA(cudaStreamWaitEvent(c->copy_in, ev_done[b], 0));
                 PIPE_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
                 if (cc) PIPE_CUDA(cudaStreamWaitEvent(s, ev_cc[b], 0));
             }
             PIPE_CUDA(cudaMemcpyAsync(c->stage_in[b].p, src + lo, in_len, cudaMemcpyHostToDevice, c->copy_in));
-            PIPE_CUDA(cudaEventRecord(ev_up[b], c->copy_in));
+            PIPE_CUDA(cudaEventRecord(ev_up[b], c->copy_in));                 // also covers the index upload (same stream)
             PIPE_CUDA(cudaStreamWaitEvent(s, ev_up[b], 0));
             const uint64_t* d_off = c->walk_off.as<uint64_t>() + i0;
             const uint32_t* d_hdr = c->walk_hdr.as<uint32_t>() + i0;
@@ -285,15 +300,15 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
             const uint64_t out_room = std::min<uint64_t>((uint64_t)cnt * bs, cap - (uint64_t)i0 * bs);
             OutSet o; o.base = c->stage_out[b].as<uint8_t>(); o.off = nullptr; o.cap = nullptr; o.stride = bs; o.total = out_room;
             o.slot_cap = (uint32_t)bs;
-            PIPE_CUDA(launch_decompress(in, o, d_hdr, d_len, d_st, (uint32_t)cnt, nullptr, 0, c->d_ticket(), c->num_sms, s));
+            PIPE_CUDA(launch_decompress(in, o, d_hdr, d_len, d_st, (uint32_t)cnt, nullptr, 0, w.ticket, c->num_sms, s));
             PIPE_CUDA(launch_decode_summary(d_len, d_st, d_sum, d_in, d_off, d_hdr, (uint32_t)cnt, (uint32_t)bs, bc ? 1 : 0,
-                                            c->d_summary(), s));
-            PIPE_CUDA(cudaMemcpyAsync(&c->h()->pipe_summary[k & 3], c->d_summary(), sizeof(DecodeSummary), cudaMemcpyDeviceToHost, s));
+                                            w.summary, s));
+            PIPE_CUDA(cudaMemcpyAsync(&c->h()->pipe_summary[k & 3], w.summary, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, s));
             PIPE_CUDA(cudaEventRecord(ev_done[b], s));
         }
-        if (k >= 1) {
-            const size_t kk = k - 1;
-            const int b = (int)(kk & 1);
+        if (k >= lead) {
+            const size_t kk = k - lead;
+            const int b = (int)(kk % PIPE_DEPTH);
             PIPE_CUDA(cudaEventSynchronize(ev_done[b]));
             const DecodeSummary sm = c->h()->pipe_summary[kk & 3];
             const bool last = kk + 1 == nchunks;
@@ -310,17 +325,14 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
             total = cfirst[kk] * bs + sm.total;
         }
     }
-    if (unusual) {
-        cudaStreamSynchronize(s); cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side);
-        return 0;
-    }
+    if (unusual) { pipe_drain(c); return 0; }
     if (cc) {
         PIPE_CUDA(launch_xxh32_final(c->d_xxh(), c->d_content_sum(), c->side));
         PIPE_CUDA(cudaMemcpyAsync(&c->h()->content_sum, c->d_content_sum(), 4, cudaMemcpyDeviceToHost, c->side));
         PIPE_CUDA(cudaStreamSynchronize(c->side));
     }
     PIPE_CUDA(cudaStreamSynchronize(c->copy_out));
-    PIPE_CUDA(cudaStreamSynchronize(s));
+    pipe_drain(c);
 #undef PIPE_CUDA
     if (cc && rd32(src + p) != c->h()->content_sum) { *rc_out = B2LZ4F_ERR_CONTENT_CHECKSUM_INVALID; return 1; }   // :625-635
     *out = total;
