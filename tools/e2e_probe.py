@@ -16,7 +16,7 @@ hback = torch.empty(n, dtype=torch.uint8).pin_memory()
 import ctypes as C
 def arr(t, k): return np.frombuffer((C.c_uint8 * k).from_address(t.data_ptr()), dtype=np.uint8)
 hs, hd, hb = arr(host, n), arr(hcomp, cap), arr(hback, n)
-for label, env in (("pipelined", {}), ("blocks8192", {"B2_PIPE_BLOCKS": "8192"}), ("blocks2048", {"B2_PIPE_BLOCKS": "2048"}), ("oneshot", {"B2_NO_PIPELINE": "1"})):
+for label, env in (("pipelined", {}), ("blocks1024", {"B2_PIPE_BLOCKS": "1024"}), ("blocks512", {"B2_PIPE_BLOCKS": "512"}), ("blocks4096", {"B2_PIPE_BLOCKS": "4096"}), ("oneshot", {"B2_NO_PIPELINE": "1"})):
     for k in ("B2_PIPE_BLOCKS", "B2_NO_PIPELINE"): os.environ.pop(k, None)
     os.environ.update(env)
     for it in range(3):
