@@ -75,24 +75,26 @@ __device__ __forceinline__ uint32_t chunk_mask(const IdxParams& P, uint64_t chun
     uint32_t w4 = 0;
     if (cbase + 16 < span) w4 = __ldg(reinterpret_cast<const uint32_t*>(P.a0 + cbase + 16));
     const uint32_t w[5] = {A.x, A.y, A.z, A.w, w4};
+    // cheap filter first: a non-zero word whose size field is within the bound (random bytes pass with
+    // probability 2 * bound / 2^32); position range, record fit and the hop test only for those
     uint32_t mask = 0;
 #pragma unroll
     for (int b = 0; b < 16; b++) {
         const uint32_t h = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1], (b & 3) * 8);
-        const uint32_t sz = h & 0x7FFFFFFFu;
-        const int64_t p = (int64_t)(cbase + b) - (int64_t)P.lead;   // position in the frame
-        const bool ok = h != 0 && sz <= P.bound && p >= (int64_t)P.start &&
-                        (uint64_t)p + 4 + sz + P.trailer <= P.n;
+        const bool ok = h != 0 && (h & 0x7FFFFFFFu) <= P.bound;
         mask |= ok ? (1u << b) : 0u;
     }
     uint32_t m = mask;
-    while (m) {                                              // rare: prune what does not lead anywhere
+    while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
         const uint32_t h = __funnelshift_r(b < 4 ? w[0] : b < 8 ? w[1] : b < 12 ? w[2] : w[3],
                                            b < 4 ? w[1] : b < 8 ? w[2] : b < 12 ? w[3] : w[4], (b & 3) * 8);
-        const uint64_t p = cbase + b - P.lead;
-        if (!leads_somewhere(P, p, h & 0x7FFFFFFFu)) mask &= ~(1u << b);
+        const uint32_t sz = h & 0x7FFFFFFFu;
+        const int64_t p = (int64_t)(cbase + b) - (int64_t)P.lead;   // position in the frame
+        const bool ok = p >= (int64_t)P.start && (uint64_t)p + 4 + sz + P.trailer <= P.n &&
+                        leads_somewhere(P, (uint64_t)p, sz);
+        if (!ok) mask &= ~(1u << b);
     }
     return mask;
 }
