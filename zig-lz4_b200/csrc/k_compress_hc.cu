@@ -30,7 +30,7 @@
 namespace b2 {
 
 constexpr int HC_WARPS = 4;                 // warps per CTA
-constexpr int HC_CTAS_PER_SM = 2;
+constexpr int HC_CTAS_PER_SM = 8;     // 32 warps per SM: the chain walk is an L2 pointer chase, more blocks in flight = more throughput
 constexpr uint32_t HC_HASH = 32768, HC_CHAIN = 65536;
 
 struct HcWork {
