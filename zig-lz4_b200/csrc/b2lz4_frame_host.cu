@@ -116,6 +116,22 @@ static inline uint32_t rd32(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+// First block of every chunk (+ sentinel).  The pipeline's head (nothing to compute until the first upload is
+// in) and tail (nothing to overlap the last download with) shrink with the chunk, so decode chunks ramp up
+// (1/4, 1/2 of the nominal size) and down again at the end.
+static std::vector<size_t> chunk_plan(size_t nb, size_t chunk_blocks, bool ramped) {
+    std::vector<size_t> first;
+    const size_t q = std::max<size_t>(1, chunk_blocks / 4), h = std::max<size_t>(1, chunk_blocks / 2);
+    size_t i = 0;
+    const bool ramp = ramped && nb >= 4 * chunk_blocks;
+    if (ramp) { first.push_back(0); first.push_back(q); i = q + h; }
+    const size_t tail = ramp ? q + h : 0;
+    while (i + tail < nb) { first.push_back(i); i += std::min(chunk_blocks, nb - tail - i); }
+    if (ramp) { first.push_back(nb - q - h); first.push_back(nb - q); }
+    first.push_back(nb);
+    return first;
+}
+
 constexpr int PIPE_DEPTH = 3;   // chunks in flight: staging buffers, workspaces and compute streams
 
 static void pipe_drain(b2lz4_ctx* c) {
@@ -131,7 +147,9 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
     size_t hsize = 0;
     { int rc = b2lz4f_write_frame_header(dst, cap, prefs, &hsize); if (rc) return rc; }      // src/lz4f.zig:369
     const size_t chunk = chunk_blocks * bs;
-    const size_t nchunks = (n + chunk - 1) / chunk;
+    // uniform chunks: a compress chunk is only done when its slowest block is (~6 ms), smaller chunks just add such waits
+    const std::vector<size_t> cfirst = chunk_plan((n + bs - 1) / bs, chunk_blocks, false);
+    const size_t nchunks = cfirst.size() - 1;
     const size_t rec_bound = 4 + compress_bound(bs) + (bc ? 4 : 0);
     const size_t out_bound = (chunk / bs) * rec_bound;
     // HC keeps its chain tables per resident warp in one shared buffer: its chunks run on one stream
@@ -153,7 +171,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
             const int b = (int)(k % PIPE_DEPTH);
             const b2_ws_ref w = c->ws(nws == 1 ? 0 : b);
             cudaStream_t s = w.stream;
-            const size_t o = k * chunk, len = std::min(chunk, n - o);
+            const size_t o = cfirst[k] * bs, len = std::min(cfirst[k + 1] * bs, n) - o;
             if (k >= (size_t)PIPE_DEPTH) {                   // buffers of chunk k - DEPTH must be free again
                 B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_done[b], 0));
                 if (cc) B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_cc[b], 0));
@@ -236,9 +254,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
     if (cap < (nb - 1) * bs + 1) return 0;                       // optimistic layout needs room for every block start
     size_t chunk_blocks;
     if (!pipeline_applies(nb * bs, bs, &chunk_blocks)) return 0;
-    std::vector<size_t> cfirst;                                  // first block of each chunk (+ sentinel)
-    for (size_t i = 0; i < nb; i += chunk_blocks) cfirst.push_back(i);
-    cfirst.push_back(nb);
+    const std::vector<size_t> cfirst = chunk_plan(nb, chunk_blocks, true);   // first block of each chunk (+ sentinel)
     const size_t nchunks = cfirst.size() - 1;
     size_t max_in = 0, max_blocks = 0;
     for (size_t k = 0; k < nchunks; k++) {
