@@ -31,7 +31,6 @@
 namespace b2 {
 
 constexpr int K1_WARPS = 4;
-constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int HASH_ENTRIES = 4096;  // LZ4_HASH_SIZE_U32, src/lz4.zig:33
 
 __device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * HASH_MULTIPLIER) >> 20; }  // :75-77
@@ -46,12 +45,6 @@ __device__ __forceinline__ uint32_t ld_u32x(const uint8_t* __restrict__ p) {
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// Pulls the 32-byte sector that holds *p into L1 (result unused; nothing ever waits on it).
-__device__ __forceinline__ void touch_sector(const uint8_t* p) {
-    uint32_t d;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d) : "l"(p));
-}
-
 // F(x) = sum_{u<x} (u >> 6): cumulative step of the reference's `step = searchMatchNb >> 6` schedule.
 __device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
     uint32_t A = x >> 6, B = x & 63;
@@ -116,12 +109,7 @@ __device__ void compress_block_general(const uint8_t* __restrict__ src, uint32_t
                 uint32_t pp = __shfl_sync(FULL, p, sl);
                 if (prev) cand = pp;                             // what an earlier iteration just put()
                 bool valid = active && cand > 0 && cand < p && cand + MAX_DISTANCE >= p;  // :345-347
-                if (valid) {
-                    const uint8_t* cp = src + cand;
-                    // the extension reads [cand + 4, cand + 20) next: bring its second sector along
-                    if ((reinterpret_cast<uintptr_t>(cp) & 31u) > 12u && cand + 19 < n) touch_sector(cp + 19);
-                    valid = (ld_u32x(cp) == v);                  // :348
-                }
+                if (valid) valid = (ld_u32x(src + cand) == v);   // :348
                 uint32_t vm = __ballot_sync(FULL, valid);
                 uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
                 uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
