@@ -106,6 +106,12 @@ B2LZ4_API int b2lz4_decompress_safe(const void* src, size_t n, void* dst, size_t
 /* replaces lz4.decompressSafeUsingDict — reference src/lz4.zig:960-964 */
 B2LZ4_API int b2lz4_decompress_safe_using_dict(const void* src, size_t n, void* dst, size_t cap,
                                                const void* dict, size_t dict_len, size_t* out);
+/* Dictionary compression, the encode side of decompressSafeUsingDict.  The reference's Stream.loadDict +
+ * compressFastContinue (src/lz4.zig:798-836) accept a dictionary but never match into it; this is
+ * the same matcher with the table primed by the last 64 KiB of `dict`.  Output decodes with
+ * lz4.decompressSafeUsingDict(…, dict); with dict_len == 0 it is byte-identical to lz4.compressFast. */
+B2LZ4_API int b2lz4_compress_fast_using_dict(const void* src, size_t n, void* dst, size_t cap, const void* dict,
+                                             size_t dict_len, uint32_t acceleration, size_t* out);
 /* replaces lz4hc.compressHC — reference src/lz4hc.zig:1440-1453 (levels 3..9; <2 -> 9) */
 B2LZ4_API int b2lz4_compress_hc(const void* src, size_t n, void* dst, size_t cap, int level, size_t* out);
 /* XXH32 as used by lz4f through std.hash.XxHash32 — reference src/lz4f.zig:139,424,438 */
@@ -132,6 +138,17 @@ B2LZ4_API int b2lz4_compress_hc_batch_dev(b2lz4_ctx* ctx, const void* src, const
                                           const uint32_t* src_len, void* dst, const uint64_t* dst_off,
                                           const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
                                           size_t nblocks, int level, void* stream);
+/* many records against one shared dictionary (BASELINE configs[4] record case); device / host pointers */
+B2LZ4_API int b2lz4_compress_fast_dict_batch_dev(b2lz4_ctx* ctx, const void* src, const uint64_t* src_off,
+                                                 const uint32_t* src_len, void* dst, const uint64_t* dst_off,
+                                                 const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
+                                                 size_t nblocks, const void* dict, size_t dict_len,
+                                                 uint32_t acceleration, void* stream);
+B2LZ4_API int b2lz4_compress_fast_dict_batch(b2lz4_ctx* ctx, const void* src, const uint64_t* src_off,
+                                             const uint32_t* src_len, void* dst, const uint64_t* dst_off,
+                                             const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
+                                             size_t nblocks, const void* dict, size_t dict_len,
+                                             uint32_t acceleration);
 B2LZ4_API int b2lz4_compress_fast_batch(b2lz4_ctx* ctx, const void* src, const uint64_t* src_off,
                                         const uint32_t* src_len, void* dst, const uint64_t* dst_off,
                                         const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,

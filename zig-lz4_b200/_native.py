@@ -83,6 +83,7 @@ EXPORTS = [
     "b2lz4_decompress_safe_using_dict", "b2lz4_compress_hc", "b2lz4_xxh32",
     "b2lz4_compress_fast_batch_dev", "b2lz4_decompress_safe_batch_dev", "b2lz4_compress_hc_batch_dev",
     "b2lz4_compress_fast_batch", "b2lz4_decompress_safe_batch", "b2lz4_compress_hc_batch", "b2lz4_xxh32_dev",
+    "b2lz4_compress_fast_using_dict", "b2lz4_compress_fast_dict_batch", "b2lz4_compress_fast_dict_batch_dev",
     "b2lz4f_prefs_init", "b2lz4f_compress_frame_bound", "b2lz4f_compress_frame", "b2lz4f_decompress_frame",
     "b2lz4f_header_size", "b2lz4f_write_frame_header", "b2lz4f_parse_frame_header",
     "b2lz4f_compress_frame_ctx", "b2lz4f_decompress_frame_ctx", "b2lz4f_compress_frame_dev",
@@ -126,12 +127,15 @@ def lib():
     L.b2lz4_decompress_safe.argtypes = [vp, sz, vp, sz, szp]
     L.b2lz4_decompress_safe_using_dict.argtypes = [vp, sz, vp, sz, vp, sz, szp]
     L.b2lz4_compress_hc.argtypes = [vp, sz, vp, sz, i32, szp]
+    L.b2lz4_compress_fast_using_dict.argtypes = [vp, sz, vp, sz, vp, sz, u32, szp]
     L.b2lz4_xxh32.argtypes = [vp, sz, u32, C.POINTER(u32)]
     batch = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
     L.b2lz4_compress_fast_batch_dev.argtypes = batch + [u32, vp]
     L.b2lz4_decompress_safe_batch_dev.argtypes = batch + [vp, sz, vp]
     L.b2lz4_compress_hc_batch_dev.argtypes = batch + [i32, vp]
     L.b2lz4_compress_fast_batch.argtypes = batch + [u32]
+    L.b2lz4_compress_fast_dict_batch.argtypes = batch + [vp, sz, u32]
+    L.b2lz4_compress_fast_dict_batch_dev.argtypes = batch + [vp, sz, u32, vp]
     L.b2lz4_decompress_safe_batch.argtypes = batch + [vp, sz]
     L.b2lz4_compress_hc_batch.argtypes = batch + [i32]
     L.b2lz4_xxh32_dev.argtypes = [vp, vp, sz, u32, vp, vp]
@@ -326,6 +330,13 @@ class Context:
     def compress_fast_batch(self, src, src_off, src_len, dst_total, dst_off, dst_cap, accel=1):
         return self._host_batch(lib().b2lz4_compress_fast_batch, src, src_off, src_len, dst_total, dst_off, dst_cap,
                                 (accel,))
+
+    def compress_fast_dict_batch(self, src, src_off, src_len, dst_total, dst_off, dst_cap, dict, accel=1):
+        """records against one shared dictionary; decode with decompress_safe_batch(..., dict=dict)"""
+        dp, dn, keep = as_buffer(dict)
+        extra = (dp if dn else 0, dn, accel)
+        return self._host_batch(lib().b2lz4_compress_fast_dict_batch, src, src_off, src_len, dst_total, dst_off, dst_cap,
+                                extra)
 
     def decompress_safe_batch(self, src, src_off, src_len, dst_total, dst_off, dst_cap, dict=None):
         if dict is None:

@@ -13,6 +13,11 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
                                  uint32_t nblocks, uint32_t max_len, uint32_t accel, uint32_t* ticket, int num_sms,
                                  cudaStream_t stream);
 
+// fast compressor with a shared dictionary (k_compress_dict.cu); primed: 4096 u32 of device scratch
+cudaError_t launch_compress_fast_dict(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
+                                      uint32_t nblocks, const uint8_t* dict, uint64_t dict_len, uint32_t* primed,
+                                      uint32_t accel, uint32_t* ticket, int num_sms, cudaStream_t stream);
+
 // K2 — decompressor (k_decompress.cu).  hdr: optional frame block headers (bit31 = stored raw).
 cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint32_t* hdr, uint32_t* out_len,
                               int32_t* status, uint32_t nblocks, const uint8_t* dict, uint32_t dict_len,

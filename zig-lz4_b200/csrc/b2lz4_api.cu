@@ -69,7 +69,7 @@ int b2_hc_supported(int level) { return hc_nb_searches(level) >= 0 ? 1 : 0; }
 
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
-               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap;
+               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap + dict_table.cap;
     for (int i = 0; i < 3; i++) t += stage_in[i].cap + stage_out[i].cap;
     for (int i = 0; i < 2; i++) t += x_slots[i].cap + x_csize[i].cap + x_status[i].cap + x_sums[i].cap + x_rec_off[i].cap + x_small[i].cap;
     return t;
@@ -140,7 +140,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->slots, &c->csize, &c->status, &c->sums, &c->rec_off, &c->small, &c->walk_off, &c->walk_hdr,
-                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
+                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->dict_table, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
                       &c->stage_out[0], &c->stage_out[1], &c->stage_out[2], &c->stage_aux,
                       &c->x_slots[0], &c->x_slots[1], &c->x_csize[0], &c->x_csize[1], &c->x_status[0], &c->x_status[1],
                       &c->x_sums[0], &c->x_sums[1], &c->x_rec_off[0], &c->x_rec_off[1], &c->x_small[0], &c->x_small[1]};
@@ -685,6 +685,21 @@ int b2lz4_compress_fast_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t*
     return B2LZ4_OK;
 }
 
+int b2lz4_compress_fast_dict_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* src_off, const uint32_t* src_len, void* dst,
+                                       const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
+                                       size_t nblocks, const void* dict, size_t dict_len, uint32_t accel, void* stream) {
+    if (!c) return B2LZ4F_ERR_PARAMETER_NULL;
+    if (nblocks > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(c->dict_table.ensure(4096 * 4));
+    B2_CUDA(launch_compress_fast_dict(explicit_in(src, src_off, src_len), explicit_out(dst, dst_off, dst_cap), out_len, status,
+                                      (uint32_t)nblocks, (const uint8_t*)dict, dict ? dict_len : 0, c->dict_table.as<uint32_t>(),
+                                      accel, c->d_ticket(), c->num_sms, s));
+    return B2LZ4_OK;
+}
+
 int b2lz4_decompress_safe_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* src_off, const uint32_t* src_len, void* dst,
                                     const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
                                     size_t nblocks, const void* dict, size_t dict_len, void* stream) {
@@ -730,7 +745,7 @@ int b2lz4_xxh32_dev(b2lz4_ctx* c, const void* src, size_t n, uint32_t seed, uint
 // ================================================================ host-pointer batch / block API
 namespace {
 
-enum class Op { Fast, Decode, HC };
+enum class Op { Fast, Decode, HC, FastDict };
 
 // Stages a host batch through the device: one H2D of the byte span the blocks cover, the kernel, one
 // D2H of the span the outputs cover.
@@ -776,6 +791,11 @@ static int host_batch(b2lz4_ctx* c, Op op, int param, const void* srcv, const ui
     OutSet out = explicit_out(c->stage_out[0].p, d_doff, d_dcap);
     if (op == Op::Fast) {
         B2_CUDA(launch_compress_fast(in, out, d_olen, d_stat, (uint32_t)nb, max_len, (uint32_t)param, c->d_ticket(), c->num_sms, s));
+    } else if (op == Op::FastDict) {
+        B2_CUDA(c->dict_table.ensure(4096 * 4));
+        B2_CUDA(launch_compress_fast_dict(in, out, d_olen, d_stat, (uint32_t)nb, (dict && dict_len) ? d_dict : nullptr,
+                                          dict ? dict_len : 0, c->dict_table.as<uint32_t>(), (uint32_t)param, c->d_ticket(),
+                                          c->num_sms, s));
     } else if (op == Op::Decode) {
         B2_CUDA(launch_decompress(in, out, nullptr, d_olen, d_stat, (uint32_t)nb, dict ? d_dict : nullptr, (uint32_t)dict_len,
                                   c->d_ticket(), c->num_sms, s));
@@ -831,6 +851,11 @@ int b2lz4_compress_fast_batch(b2lz4_ctx* c, const void* src, const uint64_t* so,
                               const uint32_t* dc, uint32_t* ol, int32_t* st, size_t nb, uint32_t accel) {
     return host_batch(c, Op::Fast, (int)accel, src, so, sl, dst, dofs, dc, ol, st, nb, nullptr, 0);
 }
+int b2lz4_compress_fast_dict_batch(b2lz4_ctx* c, const void* src, const uint64_t* so, const uint32_t* sl, void* dst, const uint64_t* dofs,
+                                   const uint32_t* dc, uint32_t* ol, int32_t* st, size_t nb, const void* dict, size_t dict_len,
+                                   uint32_t accel) {
+    return host_batch(c, Op::FastDict, (int)accel, src, so, sl, dst, dofs, dc, ol, st, nb, dict, dict ? dict_len : 0);
+}
 int b2lz4_decompress_safe_batch(b2lz4_ctx* c, const void* src, const uint64_t* so, const uint32_t* sl, void* dst, const uint64_t* dofs,
                                 const uint32_t* dc, uint32_t* ol, int32_t* st, size_t nb, const void* dict, size_t dict_len) {
     return host_batch(c, Op::Decode, 0, src, so, sl, dst, dofs, dc, ol, st, nb, dict, dict_len);
@@ -854,6 +879,10 @@ int b2lz4_decompress_safe(const void* src, size_t n, void* dst, size_t cap, size
 int b2lz4_decompress_safe_using_dict(const void* src, size_t n, void* dst, size_t cap, const void* dict, size_t dict_len, size_t* out) {
     static const uint8_t empty = 0;
     return host_single(Op::Decode, 0, src, n, dst, cap, dict ? dict : &empty, dict_len, out);
+}
+int b2lz4_compress_fast_using_dict(const void* src, size_t n, void* dst, size_t cap, const void* dict, size_t dict_len,
+                                   uint32_t accel, size_t* out) {
+    return host_single(Op::FastDict, (int)accel, src, n, dst, cap, dict, dict ? dict_len : 0, out);
 }
 int b2lz4_compress_hc(const void* src, size_t n, void* dst, size_t cap, int level, size_t* out) {
     if (!out) return B2LZ4F_ERR_PARAMETER_NULL;

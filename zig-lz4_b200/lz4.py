@@ -53,6 +53,15 @@ def compressDefault(src, dst_capacity=None):
     return compressFast(src, ACCELERATION_DEFAULT, dst_capacity)
 
 
+def compressFastUsingDict(src, dict, acceleration=1, dst_capacity=None):
+    """compressFast with the table primed by `dict` (what Stream.loadDict promises, reference src/lz4.zig:798-836, but
+    never delivers — SURVEY F6).  Decode with decompressSafeUsingDict(…, dict); an empty dict gives compressFast's bytes."""
+    n = len(memoryview(src).cast("B")) if not isinstance(src, bytes) else len(src)
+    cap = compressBound(n) if dst_capacity is None else dst_capacity
+    dp, dn, dkeep = as_buffer(dict)
+    return _call_out(lib().b2lz4_compress_fast_using_dict, src, cap, dp if dn else 0, dn, acceleration)
+
+
 def decompressSafe(src, dst_capacity):
     """reference src/lz4.zig:257-259"""
     return _call_out(lib().b2lz4_decompress_safe, src, dst_capacity)
