@@ -27,6 +27,7 @@
 // Blocks are handed to warps through a global ticket so long and short blocks balance.
 #include "b2_common.cuh"
 #include "b2_kernels.h"
+#include <cstdlib>
 
 namespace b2 {
 
@@ -550,7 +551,8 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
     //   u16 tables (8 KiB / warp):  CTAs of 3 warps, 9 per SM -> 27 blocks in flight
     //   u32 tables (16 KiB / warp): CTAs of 1 warp, 13 per SM -> 13 blocks in flight
     const int warps = small ? 3 : 1;
-    const int ctas_per_sm = small ? 9 : 13;
+    int ctas_per_sm = small ? 9 : 13;
+    if (const char* e = getenv("B2_K1_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas_per_sm) ctas_per_sm = v; }   // occupancy experiments
     const size_t smem = (size_t)warps * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
     static bool attr_done = false;
     if (!attr_done) {
