@@ -323,6 +323,44 @@ __device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src
 
 __device__ __forceinline__ uint32_t lane_range(uint32_t a, uint32_t b) { return ((2u << b) - 1u) & ~((1u << a) - 1u); }
 
+// The search of compress_block_a1 past its first window: reference iterations j0, j0+1, ... of the search that started
+// at q (acceleration 1: step = iteration >> 6, :329-333), 32 per round, until a match (returns its position, the
+// candidate through *mcand) or the exit at :335 (returns 0xFFFFFFFF).  put()s are applied as the reference would.
+template <typename TableT>
+__device__ __noinline__ uint32_t search_later_windows(const uint8_t* __restrict__ src, TableT* table, uint32_t lim, uint32_t q,
+                                                      uint32_t j0, uint32_t lane, uint32_t* mcand_out) {
+    const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+    for (;;) {
+        uint32_t j = j0 + lane;
+        uint32_t pj, s;
+        if (j < 2) { pj = q + j; s = j == 0 ? 1u : 0u; }     // iterations 1 and 2 (only when lo == 31, 30)
+        else { uint32_t x = j + 63; s = x >> 6; pj = q + 1 + step_prefix(x); }
+        bool can = (pj + s <= lim);                      // :335
+        uint32_t em = __ballot_sync(FULL, !can);
+        uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;
+        bool active = lane < E;
+        uint32_t v2 = 0, h2 = 0x80000000u | lane, cand = 0;
+        if (active) { v2 = ld_u32x(src + pj); h2 = hash4(v2); cand = table[h2]; }
+        uint32_t peers2 = __match_any_sync(FULL, h2);
+        uint32_t prev = peers2 & lt;
+        int sl = prev ? 31 - __clz(prev) : (int)lane;
+        uint32_t pp = __shfl_sync(FULL, pj, sl);
+        if (prev) cand = pp;
+        bool valid = active && cand > 0 && cand < pj && cand + MAX_DISTANCE >= pj;
+        if (valid) valid = (ld_u32x(src + cand) == v2);
+        uint32_t vm = __ballot_sync(FULL, valid);
+        uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
+        uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
+        bool commit = active && lane <= L && ((peers2 & gt & le) == 0);
+        __syncwarp();
+        if (commit) table[h2] = (TableT)pj;
+        __syncwarp();
+        if (vm) { *mcand_out = __shfl_sync(FULL, cand, L); return __shfl_sync(FULL, pj, L); }
+        if (E < 32) return 0xFFFFFFFFu;
+        j0 += 32;
+    }
+}
+
 template <typename TableT>
 __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
                                   TableT* table, uint32_t lane, uint32_t& olen, int& st) {
@@ -447,40 +485,10 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             __syncwarp();
             if (finish) break;
             if (more) {
-                // ---------------- later windows of the same search: general schedule (a0 == 1), iteration 32 - lo onwards ----------------
-                const uint32_t q = base + lo + 1;
-                uint32_t j0 = 31 - lo;
-                uint32_t mpos = 0, mcand = 0;
-                bool found = false;
-                for (;;) {
-                    uint32_t j = j0 + lane;
-                    uint32_t pj, s;
-                    if (j < 2) { pj = q + j; s = j == 0 ? 1u : 0u; }     // iterations 1 and 2 (only when lo == 31, 30)
-                    else { uint32_t x = j + 63; s = x >> 6; pj = q + 1 + step_prefix(x); }
-                    bool can = (pj + s <= lim);                      // :335
-                    uint32_t em = __ballot_sync(FULL, !can);
-                    uint32_t E = em ? (uint32_t)__ffs(em) - 1 : 32;
-                    bool active = lane < E;
-                    uint32_t v2 = 0, h2 = 0x80000000u | lane, cand = 0;
-                    if (active) { v2 = ld_u32x(src + pj); h2 = hash4(v2); cand = table[h2]; }
-                    uint32_t peers2 = __match_any_sync(FULL, h2);
-                    uint32_t prev = peers2 & lt;
-                    int sl = prev ? 31 - __clz(prev) : (int)lane;
-                    uint32_t pp = __shfl_sync(FULL, pj, sl);
-                    if (prev) cand = pp;
-                    bool valid = active && cand > 0 && cand < pj && cand + MAX_DISTANCE >= pj;
-                    if (valid) valid = (ld_u32x(src + cand) == v2);
-                    uint32_t vm = __ballot_sync(FULL, valid);
-                    uint32_t L = vm ? (uint32_t)__ffs(vm) - 1 : 31;
-                    uint32_t le = (L == 31) ? FULL : ((2u << L) - 1);
-                    bool commit = active && lane <= L && ((peers2 & gt & le) == 0);
-                    __syncwarp();
-                    if (commit) table[h2] = (TableT)pj;
-                    __syncwarp();
-                    if (vm) { mpos = __shfl_sync(FULL, pj, L); mcand = __shfl_sync(FULL, cand, L); found = true; break; }
-                    if (E < 32) break;
-                    j0 += 32;
-                }
+                // later windows of the same search (general step schedule, iteration 32 - lo onwards): out of line, rare
+                uint32_t mcand = 0;
+                const uint32_t mpos = search_later_windows<TableT>(src, table, lim, base + lo + 1, 31 - lo, lane, &mcand);
+                const bool found = mpos != 0xFFFFFFFFu;
                 if (!found) break;
                 const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
                 if (!emit_sequence<TableT>(src, dst, cap, op, anchor, mpos - anchor, ml, mpos - mcand, false, 0, lane)) {
