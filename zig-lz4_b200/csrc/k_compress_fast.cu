@@ -236,15 +236,15 @@ __device__ void compress_block_general(const uint8_t* __restrict__ src, uint32_t
 //     if none of its lanes was visited.
 // A search that reaches lane 31 without a match continues in the general schedule (iteration 32 - lo
 // onwards, where the step grows).
-// long form of a sequence (length-extension bytes and/or long literal run), :362-432
-__device__ __noinline__ bool emit_sequence_long(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cap,
-                                                uint32_t* op_io, uint32_t anchor, uint32_t LL, uint32_t ml, uint32_t offset,
-                                                uint32_t lane) {
-    const uint32_t op = *op_io;
+// long form of a sequence (length-extension bytes and/or long literal run), :362-432.  Returns the new output
+// position, or 0xFFFFFFFF if it does not fit (values, not references: a reference would pin `op` in local memory).
+__device__ __noinline__ uint32_t emit_sequence_long(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cap,
+                                                    uint32_t op, uint32_t anchor, uint32_t LL, uint32_t ml, uint32_t offset,
+                                                    uint32_t lane) {
     const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
     const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
     const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
-    if (seq_end > cap) return false;
+    if (seq_end > cap) return 0xFFFFFFFFu;
     uint8_t* o = dst + op;
     if (lane == 0) o[0] = (uint8_t)(((LL < 15 ? LL : 15u) << 4) | (ml < 15 ? ml : 15u));
     write_len_ext(o + 1, LL, nll, lane);
@@ -252,8 +252,7 @@ __device__ __noinline__ bool emit_sequence_long(const uint8_t* __restrict__ src,
     uint8_t* o2 = o + 1 + nll + LL;
     if (lane == 0) { o2[0] = (uint8_t)(offset & 0xFF); o2[1] = (uint8_t)(offset >> 8); }
     write_len_ext(o2 + 2, ml, nml, lane);
-    *op_io = seq_end;
-    return true;
+    return seq_end;
 }
 
 template <typename TableT>
@@ -271,7 +270,13 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
         if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
         op = seq_end;
     } else {
-        return emit_sequence_long(src, dst, cap, &op, anchor, LL, ml, offset, lane);
+        // the caller computes the size itself, so that `op` never depends on a call result
+        const uint32_t nll = LL >= RUN_MASK ? (LL - RUN_MASK) / 255 + 1 : 0;
+        const uint32_t nml = ml >= ML_MASK ? (ml - ML_MASK) / 255 + 1 : 0;
+        const uint32_t seq_end = op + 1 + nll + LL + 2 + nml;
+        if (seq_end > cap) return false;
+        emit_sequence_long(src, dst, cap, op, anchor, LL, ml, offset, lane);
+        op = seq_end;
     }
     return true;
 }
