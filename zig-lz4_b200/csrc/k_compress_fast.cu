@@ -418,14 +418,18 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 m3 = __funnelshift_r(w3, 0u, sh);
                 nmb = 12 - c;
             }
-            // Every lane extends its own (table) match as far as the staged bytes reach: the forward words
-            // are the reads of lanes +4, +8, +12.  mlpk = length | "bytes exhausted, continue from memory" << 8.
+            // Every lane extends its own (table) match as far as the staged bytes reach.  The forward words are
+            // the reads of lanes +4, +8, +12; for the last lanes of the window they come from one more read of
+            // the 16 positions after it (v2).  mlpk = length | "bytes exhausted, continue from memory" << 8.
             uint32_t mlpk;
             {
-                const uint32_t F1 = __shfl_down_sync(FULL, v, 4), F2 = __shfl_down_sync(FULL, v, 8), F3 = __shfl_down_sync(FULL, v, 12);
-                uint32_t nfw = (31 - lane) >> 2;                         // forward words held by lanes +4, +8, +12 ...
-                const uint32_t roomw = inwin ? (lim - p) >> 2 : 0u;      // ... that lie inside the window (position <= lim)
-                nfw = nfw < roomw ? nfw : roomw;
+                uint32_t v2 = 0;
+                if (lane < 16 && p + 32 <= lim) v2 = ld_u32x(src + p + 32);
+                const uint32_t a1 = __shfl_sync(FULL, v, lane + 4), b1 = __shfl_sync(FULL, v2, lane + 4);
+                const uint32_t a2 = __shfl_sync(FULL, v, lane + 8), b2 = __shfl_sync(FULL, v2, lane + 8);
+                const uint32_t a3 = __shfl_sync(FULL, v, lane + 12), b3 = __shfl_sync(FULL, v2, lane + 12);
+                const uint32_t F1 = lane + 4 < 32 ? a1 : b1, F2 = lane + 8 < 32 ? a2 : b2, F3 = lane + 12 < 32 ? a3 : b3;
+                uint32_t nfw = inwin ? (lim - p) >> 2 : 0u;              // forward words at positions <= lim
                 nfw = nfw < 3 ? nfw : 3;
                 const uint32_t navail = 4 * nfw < nmb ? 4 * nfw : nmb;
                 const uint32_t x1 = F1 ^ m1, x2 = F2 ^ m2, x3 = F3 ^ m3;
