@@ -460,7 +460,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 V |= lane_range(lo + 1, L);
                 const uint32_t mpos = base + L;
                 const uint32_t mcand = __shfl_sync(FULL, pv ? base + (uint32_t)pl : old, L);
-                const uint32_t LL = L - lo;                              // anchor == base + lo
+                const uint32_t LL = mpos - anchor;                       // anchor == base + lo, except in a chained window's first search
                 uint32_t ml;
                 if (mcand < base) {                                      // table candidate: extension already measured
                     const uint32_t pk = __shfl_sync(FULL, mlpk, L);
@@ -470,7 +470,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                     ml = extend_bytes(src, mpos + MINMATCH, mcand + MINMATCH, mlimit, lane);
                 }
                 const uint32_t litb = __shfl_sync(FULL, v, lo + lane - 1) & 0xFFu;   // lane t (1..LL): src[anchor + t - 1]
-                if (!emit_sequence<TableT>(src, dst, cap, op, base + lo, LL, ml, mpos - mcand, true, litb, lane)) {
+                if (!emit_sequence<TableT>(src, dst, cap, op, anchor, LL, ml, mpos - mcand, anchor == base + lo, litb, lane)) {
                     st = ST_OUTPUT_TOO_SMALL;
                     return;
                 }
@@ -493,10 +493,18 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             }
             __syncwarp();
             if (finish) break;
+            if (more && base + 31 - anchor <= 33 && base + 128 <= lim) {
+                // The search goes on past lane 31 after fewer than 34 iterations: its next 31 iterations still visit
+                // consecutive positions (step 1 up to iteration 64), so they are one more ordinary window whose lane 0
+                // is the position just visited (re-putting it is a no-op).  anchor stays behind the window.
+                e = base + 31;
+                continue;
+            }
             if (more) {
-                // later windows of the same search (general step schedule, iteration 32 - lo onwards): out of line, rare
+                // later windows of the same search (it started at anchor + 1 and has visited everything up to base + 31):
+                // general step schedule, out of line, rare
                 uint32_t mcand = 0;
-                const uint32_t mpos = search_later_windows<TableT>(src, table, lim, base + lo + 1, 31 - lo, lane, &mcand);
+                const uint32_t mpos = search_later_windows<TableT>(src, table, lim, anchor + 1, base + 31 - anchor, lane, &mcand);
                 const bool found = mpos != 0xFFFFFFFFu;
                 if (!found) break;
                 const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
