@@ -323,6 +323,9 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
         uint8_t* dst; uint32_t cap;
         in.get(blk, src, n);
         out.get(blk, dst, cap);
+        // keep the two block pointers in registers (otherwise every access re-adds base + offset from the constant bank)
+        asm volatile("" : "+l"(src));
+        asm volatile("" : "+l"(dst));
         uint32_t olen = 0; int st = ST_OK;
         if (hdr && (hdr[blk] & 0x80000000u)) {
             // stored block: reference src/lz4f.zig:603-608
