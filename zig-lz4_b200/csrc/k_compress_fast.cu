@@ -263,11 +263,10 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
         // short form: token | literals | offset = LL + 3 <= 17 bytes, one byte per lane
         const uint32_t seq_end = op + LL + 3;
         if (seq_end > cap) return false;                         // monotone in op: see DESIGN.md
-        uint32_t bv = (LL << 4) | ml;
-        if (lane >= 1 && lane <= LL) bv = lit_in_lanes ? litb : (uint32_t)__ldg(src + anchor + lane - 1);
-        else if (lane == LL + 1) bv = offset;
-        else if (lane == LL + 2) bv = offset >> 8;
-        if (lane < LL + 3) dst[op + lane] = (uint8_t)bv;
+        const int32_t t = (int32_t)lane - 1 - (int32_t)LL;           // < 0: token / literal lanes, 0 and 1: offset bytes
+        uint32_t bv = t >= 0 ? offset >> (8 * t) : (lit_in_lanes ? litb : (uint32_t)__ldg(src + anchor + (lane ? lane - 1 : 0)));
+        if (lane == 0) bv = (LL << 4) | ml;
+        if (t < 2) dst[op + lane] = (uint8_t)bv;
         op = seq_end;
     } else {
         // the caller computes the size itself, so that `op` never depends on a call result
@@ -438,20 +437,21 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 const bool more_bytes = d >= navail && p + MINMATCH + navail < mlimit;
                 mlpk = (d < navail ? d : navail) | (more_bytes ? 0x100u : 0u);
             }
+            const bool plt = p < lim;           // (implies inwin)
             uint32_t lo = 0, V = 1u;            // lane `lo`: last put(); V: lanes the reference has visited
             bool finish = false, more = false;  // finish: the block's search loop is over; more: search continues past lane 31
             for (;;) {
                 // lanes lo+1.. are iterations 1.. of the search that starts at e + lo + 1 (< lim)
-                const bool elig = inwin && lane > lo && (p < lim || lane == lo + 2);
+                const bool elig = lane > lo && (plt || (inwin && lane == lo + 2));
                 // candidate: nearest earlier lane of the same bucket that has been visited when this lane is probed
                 const uint32_t seen = V | ~((2u << lo) - 1u);            // visited so far + every lane after lo (probed before me)
                 const uint32_t pv = peers & lt & seen;
                 const int pl = pv ? 31 - __clz(pv) : (int)lane;
                 const uint32_t pvv = __shfl_sync(FULL, v, pl);
                 const bool valid = elig && (pv ? (pvv == v && base + pl > 0) : vold);
-                const uint32_t em = __ballot_sync(FULL, elig);           // a prefix range lo+1..hiE (may be empty)
                 const uint32_t m = __ballot_sync(FULL, valid);
                 if (m == 0) {
+                    const uint32_t em = __ballot_sync(FULL, elig);       // a prefix range lo+1..hiE (may be empty)
                     V |= em;
                     if (em & 0x80000000u) more = true; else finish = true;   // ran off the window / hit the exit at :335
                     break;
