@@ -260,7 +260,6 @@ def main():
     t_all1.record(stream)
     barrier()
     launches = z.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = t_all0.elapsed_time(t_all1)
     if world > 1:
         t = torch.tensor([total_ms, tc, td], dtype=torch.float64, device=dev)
@@ -315,6 +314,7 @@ def main():
                "d2h_bytes_per_step": world * (cs + n), "ms_per_step": round(dt / args.steps * 1e3, 3),
                "api": "b2lz4f_compress_frame_ctx + b2lz4f_decompress_frame_ctx (host pointers, pinned)"}
 
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and e2e)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
