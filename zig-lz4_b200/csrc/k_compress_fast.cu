@@ -557,6 +557,8 @@ __global__ void __launch_bounds__(96, 9) k_compress_fast(BlockSet in, OutSet out
         // keep the two block pointers in registers (otherwise every access re-adds base + offset from the constant bank)
         asm volatile("" : "+l"(src));
         asm volatile("" : "+l"(dst));
+        __builtin_assume(__isGlobal(src));
+        __builtin_assume(__isGlobal(dst));
         uint32_t olen; int st;
         compress_block<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
         if (lane == 0) {

@@ -227,9 +227,18 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                 const uint32_t mx = __reduce_max_sync(FULL, nl);
                 const uint8_t* ls = src + myLit;
                 uint8_t* ld = dst + o0;
-#pragma unroll 4
-                for (uint32_t i = 0; i < mx; i++)
-                    if (i < nl) ld[i] = __ldg(ls + i);
+                uint32_t rem = nl;
+                for (uint32_t i0 = 0; i0 < mx; i0 += 4) {
+                    uint32_t r[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if ((uint32_t)u < rem) r[u] = __ldg(ls + u);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if ((uint32_t)u < rem) ld[u] = (uint8_t)r[u];
+                    ls += 4; ld += 4;
+                    rem = rem > 4 ? rem - 4 : 0u;
+                }
                 uint32_t lm = __ballot_sync(FULL, lng);
                 while (lm) {
                     const int j = __ffs(lm) - 1;
@@ -266,14 +275,21 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                         // self-overlapping match with offset >= 8: a chunk only reads bytes of earlier chunks.
                         const uint32_t nm = (go && !lng && !tiny) ? myML : 0u;
                         const uint32_t mx = __reduce_max_sync(FULL, nm);
+                        // one pair of running pointers and one remaining-byte count per lane: the accesses are
+                        // base + immediate under a predicate (not a re-derived 64-bit address per byte)
+                        const uint8_t* ps = msrc;
+                        uint8_t* pd = md;
+                        uint32_t rem = nm;
                         for (uint32_t i0 = 0; i0 < mx; i0 += 8) {
                             uint32_t r[8];
 #pragma unroll
                             for (int u = 0; u < 8; u++)
-                                if (i0 + u < nm) r[u] = msrc[i0 + u];
+                                if ((uint32_t)u < rem) r[u] = ps[u];
 #pragma unroll
                             for (int u = 0; u < 8; u++)
-                                if (i0 + u < nm) md[i0 + u] = (uint8_t)r[u];
+                                if ((uint32_t)u < rem) pd[u] = (uint8_t)r[u];
+                            ps += 8; pd += 8;
+                            rem = rem > 8 ? rem - 8 : 0u;
                         }
                     }
                     if (__ballot_sync(FULL, go && tiny)) {
@@ -326,6 +342,8 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
         // keep the two block pointers in registers (otherwise every access re-adds base + offset from the constant bank)
         asm volatile("" : "+l"(src));
         asm volatile("" : "+l"(dst));
+        __builtin_assume(__isGlobal(src));
+        __builtin_assume(__isGlobal(dst));
         uint32_t olen = 0; int st = ST_OK;
         if (hdr && (hdr[blk] & 0x80000000u)) {
             // stored block: reference src/lz4f.zig:603-608
