@@ -112,6 +112,12 @@ B2LZ4_API int b2lz4_decompress_safe_using_dict(const void* src, size_t n, void* 
  * lz4.decompressSafeUsingDict(…, dict); with dict_len == 0 it is byte-identical to lz4.compressFast. */
 B2LZ4_API int b2lz4_compress_fast_using_dict(const void* src, size_t n, void* dst, size_t cap, const void* dict,
                                              size_t dict_len, uint32_t acceleration, size_t* out);
+/* replaces lz4.compressDestSize — reference src/lz4.zig:551-616.  *src_size: in = bytes available, out = bytes
+ * consumed (the prefix the reference's bisection settles on); *out = compressed size.  dst[0..*out) is
+ * compressDefault(src[0..*src_size)): the reference leaves the bytes of its LAST probe in dst, which is a
+ * different (undecodable) stream whenever that probe did not fit — the returned sizes are the reference's,
+ * the bytes are the ones its contract (and its own test, src/test_dictionary.zig:78-103) expects. */
+B2LZ4_API int b2lz4_compress_dest_size(const void* src, void* dst, size_t cap, size_t* src_size, size_t* out);
 /* replaces lz4hc.compressHC — reference src/lz4hc.zig:1440-1453 (levels 3..9; <2 -> 9) */
 B2LZ4_API int b2lz4_compress_hc(const void* src, size_t n, void* dst, size_t cap, int level, size_t* out);
 /* XXH32 as used by lz4f through std.hash.XxHash32 — reference src/lz4f.zig:139,424,438 */
@@ -161,6 +167,18 @@ B2LZ4_API int b2lz4_compress_hc_batch(b2lz4_ctx* ctx, const void* src, const uin
                                       const uint32_t* src_len, void* dst, const uint64_t* dst_off,
                                       const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
                                       size_t nblocks, int level);
+/* compressDestSize for many blocks: src_len[i] = bytes block i may consume, dst_cap[i] = room; consumed[i] /
+ * out_len[i] as lz4.compressDestSize returns them.  Every probe of the reference's bisection is one launch of
+ * the fast compressor over all blocks.  max_src_len: an upper bound of src_len[] (0 = unknown: 31 probes). */
+B2LZ4_API int b2lz4_compress_dest_size_batch_dev(b2lz4_ctx* ctx, const void* src, const uint64_t* src_off,
+                                                 const uint32_t* src_len, void* dst, const uint64_t* dst_off,
+                                                 const uint32_t* dst_cap, uint32_t* consumed, uint32_t* out_len,
+                                                 int32_t* status, size_t nblocks, uint32_t max_src_len,
+                                                 void* stream);
+B2LZ4_API int b2lz4_compress_dest_size_batch(b2lz4_ctx* ctx, const void* src, const uint64_t* src_off,
+                                             const uint32_t* src_len, void* dst, const uint64_t* dst_off,
+                                             const uint32_t* dst_cap, uint32_t* consumed, uint32_t* out_len,
+                                             int32_t* status, size_t nblocks);
 /* XXH32 of a device buffer; asynchronous, result written to *out_dev (device u32). */
 B2LZ4_API int b2lz4_xxh32_dev(b2lz4_ctx* ctx, const void* src, size_t n, uint32_t seed, uint32_t* out_dev,
                               void* stream);

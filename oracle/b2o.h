@@ -80,6 +80,10 @@ int b2o_decompress_safe_using_dict(const uint8_t* src, size_t n, uint8_t* dst, s
                                    const uint8_t* dict, size_t dict_len,
                                    size_t* out);                       /* src/lz4.zig:960-964 */
 
+/* *src_size: in = bytes available, out = bytes consumed; dst is left as the reference leaves it (last probe) */
+int b2o_compress_dest_size(const uint8_t* src, uint8_t* dst, size_t cap, size_t* src_size,
+                           size_t* out);                               /* src/lz4.zig:551-616 */
+
 /* ---- HC (src/lz4hc.zig), levels routed to compressHashChain only (3..9; <2 -> 9) ---- */
 int b2o_compress_hc(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level,
                     size_t* out);                                      /* src/lz4hc.zig:1440-1489 */

@@ -64,6 +64,7 @@ def lib():
         L.b2o_compress_fast.argtypes = [u8p, sz, u8p, sz, C.c_uint32, szp]
         L.b2o_decompress_safe.argtypes = [u8p, sz, u8p, sz, szp]
         L.b2o_decompress_safe_using_dict.argtypes = [u8p, sz, u8p, sz, u8p, sz, szp]
+        L.b2o_compress_dest_size.argtypes = [u8p, u8p, sz, szp, szp]
         L.b2o_compress_hc.argtypes = [u8p, sz, u8p, sz, C.c_int, szp]
         L.b2o_hc_f8_guard_hits.restype = C.c_uint64
         L.b2o_xxh32.restype = C.c_uint32
@@ -129,6 +130,18 @@ def decompress_safe(src, cap, dict=None):
     if rc:
         raise OracleError(rc)
     return bytes(dst[:out.value])
+
+
+def compress_dest_size(src, cap, src_size=None):
+    """lz4.compressDestSize: returns (consumed, compressed size, dst bytes as the reference leaves them)."""
+    p, n, keep = _buf(src)
+    used = C.c_size_t(n if src_size is None else src_size)
+    dst = (C.c_uint8 * max(1, cap))()
+    out = C.c_size_t(0)
+    rc = lib().b2o_compress_dest_size(p, dst, cap, C.byref(used), C.byref(out))
+    if rc:
+        raise OracleError(rc)
+    return used.value, out.value, bytes(dst[:cap])
 
 
 def compress_hc(src, level=9, cap=None):

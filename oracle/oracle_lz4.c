@@ -264,3 +264,61 @@ int b2o_decompress_safe_using_dict(const uint8_t* src, size_t n, uint8_t* dst, s
                                    const uint8_t* dict, size_t dict_len, size_t* out) {
     return decompress_generic(src, n, dst, cap, 1, dict, dict_len, out);
 }
+
+/* src/lz4.zig:551-616 — literal restatement, including what it leaves in dst: every probe compresses into the
+   same dst, so after the call dst holds the bytes of the LAST probe (complete or cut off where it stopped
+   fitting), not necessarily those of the prefix whose sizes are returned. */
+int b2o_compress_dest_size(const uint8_t* src, uint8_t* dst, size_t cap, size_t* srcSizePtr, size_t* out) {
+    const size_t maxSrcSize = *srcSizePtr;
+    *out = 0;
+    if (maxSrcSize == 0) {                                              /* :553-556 */
+        *srcSizePtr = 0;
+        return B2O_OK;
+    }
+    const size_t maxCompressed = b2o_compress_bound(maxSrcSize);        /* :559 */
+    if (cap >= maxCompressed) {                                         /* :560-564 */
+        size_t result = 0;
+        int rc = b2o_compress_fast(src, maxSrcSize, dst, cap, 1, &result);
+        if (rc) return rc;
+        *srcSizePtr = maxSrcSize;
+        *out = result;
+        return B2O_OK;
+    }
+    size_t low = 1, high = maxSrcSize, bestSize = 0, bestCompressedSize = 0;  /* :567-570 */
+    if (cap <= maxSrcSize) {                                            /* :573-586 */
+        const size_t estimate = cap < maxSrcSize ? cap : maxSrcSize;
+        size_t size = 0;
+        if (b2o_compress_fast(src, estimate, dst, cap, 1, &size) == B2O_OK) {
+            if (size <= cap) {
+                bestSize = estimate;
+                bestCompressedSize = size;
+                low = estimate + 1;
+            } else {
+                high = estimate - 1;
+            }
+        } else {
+            high = estimate - 1;
+        }
+    }
+    while (low <= high) {                                               /* :589-612 */
+        const size_t mid = low + (high - low) / 2;
+        if (mid == 0 || mid > maxSrcSize) break;
+        size_t size = 0;
+        if (b2o_compress_fast(src, mid, dst, cap, 1, &size) == B2O_OK) {
+            if (size <= cap) {
+                bestSize = mid;
+                bestCompressedSize = size;
+                if (mid == maxSrcSize) break;
+                low = mid + 1;
+            } else {
+                high = mid - 1;
+            }
+        } else {
+            high = mid - 1;
+        }
+        if (low > maxSrcSize) break;
+    }
+    *srcSizePtr = bestSize;                                             /* :614-615 */
+    *out = bestCompressedSize;
+    return B2O_OK;
+}

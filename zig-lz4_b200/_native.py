@@ -84,6 +84,7 @@ EXPORTS = [
     "b2lz4_compress_fast_batch_dev", "b2lz4_decompress_safe_batch_dev", "b2lz4_compress_hc_batch_dev",
     "b2lz4_compress_fast_batch", "b2lz4_decompress_safe_batch", "b2lz4_compress_hc_batch", "b2lz4_xxh32_dev",
     "b2lz4_compress_fast_using_dict", "b2lz4_compress_fast_dict_batch", "b2lz4_compress_fast_dict_batch_dev",
+    "b2lz4_compress_dest_size", "b2lz4_compress_dest_size_batch", "b2lz4_compress_dest_size_batch_dev",
     "b2lz4f_prefs_init", "b2lz4f_compress_frame_bound", "b2lz4f_compress_frame", "b2lz4f_decompress_frame",
     "b2lz4f_header_size", "b2lz4f_write_frame_header", "b2lz4f_parse_frame_header",
     "b2lz4f_compress_frame_ctx", "b2lz4f_decompress_frame_ctx", "b2lz4f_compress_frame_dev",
@@ -137,6 +138,9 @@ def lib():
     L.b2lz4_compress_fast_dict_batch.argtypes = batch + [vp, sz, u32]
     L.b2lz4_compress_fast_dict_batch_dev.argtypes = batch + [vp, sz, u32, vp]
     L.b2lz4_decompress_safe_batch.argtypes = batch + [vp, sz]
+    L.b2lz4_compress_dest_size.argtypes = [vp, vp, sz, szp, szp]
+    L.b2lz4_compress_dest_size_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
+    L.b2lz4_compress_dest_size_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, u32, vp]
     L.b2lz4_compress_hc_batch.argtypes = batch + [i32]
     L.b2lz4_xxh32_dev.argtypes = [vp, vp, sz, u32, vp, vp]
     L.b2lz4f_prefs_init.argtypes = [pp]
@@ -337,6 +341,24 @@ class Context:
         extra = (dp if dn else 0, dn, accel)
         return self._host_batch(lib().b2lz4_compress_fast_dict_batch, src, src_off, src_len, dst_total, dst_off, dst_cap,
                                 extra)
+
+    def compress_dest_size_batch(self, src, src_off, src_len, dst_total, dst_off, dst_cap):
+        """lz4.compressDestSize per block: returns (dst, consumed, out_len, status)"""
+        import numpy as np
+        nb = len(src_off)
+        sp, sn, skeep = as_buffer(src)
+        so = np.ascontiguousarray(src_off, dtype=np.uint64)
+        sl = np.ascontiguousarray(src_len, dtype=np.uint32)
+        do = np.ascontiguousarray(dst_off, dtype=np.uint64)
+        dc = np.ascontiguousarray(dst_cap, dtype=np.uint32)
+        dst = np.zeros(max(1, dst_total), dtype=np.uint8)
+        used = np.zeros(max(1, nb), dtype=np.uint32)
+        ol = np.zeros(max(1, nb), dtype=np.uint32)
+        st = np.zeros(max(1, nb), dtype=np.int32)
+        check(lib().b2lz4_compress_dest_size_batch(self._h, sp, so.ctypes.data, sl.ctypes.data, dst.ctypes.data,
+                                                   do.ctypes.data, dc.ctypes.data, used.ctypes.data, ol.ctypes.data,
+                                                   st.ctypes.data, nb))
+        return dst, used[:nb], ol[:nb], st[:nb]
 
     def decompress_safe_batch(self, src, src_off, src_len, dst_total, dst_off, dst_cap, dict=None):
         if dict is None:

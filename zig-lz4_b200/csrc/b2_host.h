@@ -91,6 +91,7 @@ struct b2lz4_ctx {
     b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, hc_work;
     b2::DevBuf idx_tiles, idx_pos, idx_jump;   // parallel frame index scratch
     b2::DevBuf dict_table;                     // primed hash table of the dictionary compressor
+    b2::DevBuf ds_work;                        // compressDestSize: per-block search state + probe lengths/results
     b2::DevBuf stage_in[3], stage_out[3], stage_aux;
     // two more chunk workspaces + compute streams for the host-pointer pipeline (three chunks in flight)
     b2::DevBuf x_slots[2], x_csize[2], x_status[2], x_sums[2], x_rec_off[2], x_small[2];

@@ -18,6 +18,22 @@ cudaError_t launch_compress_fast_dict(const BlockSet& in, const OutSet& out, uin
                                       uint32_t nblocks, const uint8_t* dict, uint64_t dict_len, uint32_t* primed,
                                       uint32_t accel, uint32_t* ticket, int num_sms, cudaStream_t stream);
 
+// compressDestSize search state, one per block (k_dest_size.cu; reference src/lz4.zig:551-616)
+struct DestSizeState {
+    uint32_t low, high;    // bisection interval over prefix lengths
+    uint32_t best;         // bestSize: longest prefix that fitted so far
+    uint32_t cur;          // prefix length of the probe in flight
+    uint32_t phase;        // 0 done, 1 estimate probe, 2 bisection probe
+    int32_t err;           // status of a block that cannot run (InputTooLarge)
+};
+cudaError_t launch_dest_size_init(const uint32_t* src_len, const uint32_t* dst_cap, DestSizeState* state,
+                                  uint32_t* probe_len, uint32_t nblocks, cudaStream_t stream);
+cudaError_t launch_dest_size_step(const uint32_t* src_len, const int32_t* probe_status, DestSizeState* state,
+                                  uint32_t* probe_len, uint32_t nblocks, cudaStream_t stream);
+cudaError_t launch_dest_size_best(const DestSizeState* state, uint32_t* probe_len, uint32_t nblocks, cudaStream_t stream);
+cudaError_t launch_dest_size_finish(const DestSizeState* state, uint32_t* consumed, uint32_t* out_len, int32_t* status,
+                                    uint32_t nblocks, cudaStream_t stream);
+
 // K2 — decompressor (k_decompress.cu).  hdr: optional frame block headers (bit31 = stored raw).
 cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint32_t* hdr, uint32_t* out_len,
                               int32_t* status, uint32_t nblocks, const uint8_t* dict, uint32_t dict_len,

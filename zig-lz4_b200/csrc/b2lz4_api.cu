@@ -69,7 +69,7 @@ int b2_hc_supported(int level) { return hc_nb_searches(level) >= 0 ? 1 : 0; }
 
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
-               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap + dict_table.cap;
+               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap + dict_table.cap + ds_work.cap;
     for (int i = 0; i < 3; i++) t += stage_in[i].cap + stage_out[i].cap;
     for (int i = 0; i < 2; i++) t += x_slots[i].cap + x_csize[i].cap + x_status[i].cap + x_sums[i].cap + x_rec_off[i].cap + x_small[i].cap;
     return t;
@@ -140,7 +140,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->slots, &c->csize, &c->status, &c->sums, &c->rec_off, &c->small, &c->walk_off, &c->walk_hdr,
-                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->dict_table, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
+                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->dict_table, &c->ds_work, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
                       &c->stage_out[0], &c->stage_out[1], &c->stage_out[2], &c->stage_aux,
                       &c->x_slots[0], &c->x_slots[1], &c->x_csize[0], &c->x_csize[1], &c->x_status[0], &c->x_status[1],
                       &c->x_sums[0], &c->x_sums[1], &c->x_rec_off[0], &c->x_rec_off[1], &c->x_small[0], &c->x_small[1]};
@@ -729,6 +729,50 @@ int b2lz4_compress_hc_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* s
     return B2LZ4_OK;
 }
 
+// compressDestSize for many blocks (reference src/lz4.zig:551-616): every probe of the reference's bisection is one
+// K1 launch over all blocks with per-block prefix lengths and dst's real capacity (K1 never writes past it and
+// reports OutputTooSmall exactly when the prefix does not fit); the chosen prefixes are compressed last, so
+// dst[0..out_len) is always compressDefault(src[0..consumed)).  max_len bounds src_len[] (0 = unknown).
+static int dest_size_dev(b2lz4_ctx* c, const void* src, const uint64_t* src_off, const uint32_t* src_len, void* dst,
+                         const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* consumed, uint32_t* out_len,
+                         int32_t* status, size_t nb, uint32_t max_len, cudaStream_t s) {
+    if (nb == 0) return B2LZ4_OK;
+    B2_CUDA(c->ds_work.ensure(nb * (sizeof(DestSizeState) + 12) + 64));
+    DestSizeState* st = c->ds_work.as<DestSizeState>();
+    uint32_t* probe_len = reinterpret_cast<uint32_t*>(st + nb);
+    uint32_t* probe_out = probe_len + nb;
+    int32_t* probe_status = reinterpret_cast<int32_t*>(probe_out + nb);
+    const uint32_t n32 = (uint32_t)nb;
+    const uint32_t table_len = max_len ? max_len : 0xFFFFFFFFu;
+    // the estimate probe + one bisection probe per bit of the longest block (+1: the interval [1, max] has max values)
+    uint32_t bits = 0;
+    for (uint32_t v = max_len ? max_len : 0x7E000000u; v; v >>= 1) bits++;
+    const uint32_t probes = bits + 2;
+    B2_CUDA(launch_dest_size_init(src_len, dst_cap, st, probe_len, n32, s));
+    for (uint32_t it = 0; it < probes; it++) {
+        B2_CUDA(launch_compress_fast(explicit_in(src, src_off, probe_len), explicit_out(dst, dst_off, dst_cap), probe_out,
+                                     probe_status, n32, table_len, 1, c->d_ticket(), c->num_sms, s));
+        B2_CUDA(launch_dest_size_step(src_len, probe_status, st, probe_len, n32, s));
+    }
+    B2_CUDA(launch_dest_size_best(st, probe_len, n32, s));
+    B2_CUDA(launch_compress_fast(explicit_in(src, src_off, probe_len), explicit_out(dst, dst_off, dst_cap), out_len, status,
+                                 n32, table_len, 1, c->d_ticket(), c->num_sms, s));
+    B2_CUDA(launch_dest_size_finish(st, consumed, out_len, status, n32, s));
+    return B2LZ4_OK;
+}
+
+int b2lz4_compress_dest_size_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* src_off, const uint32_t* src_len,
+                                       void* dst, const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* consumed,
+                                       uint32_t* out_len, int32_t* status, size_t nblocks, uint32_t max_src_len,
+                                       void* stream) {
+    if (!c) return B2LZ4F_ERR_PARAMETER_NULL;
+    if (nblocks > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    return dest_size_dev(c, src, src_off, src_len, dst, dst_off, dst_cap, consumed, out_len, status, nblocks, max_src_len, s);
+}
+
 int b2lz4_xxh32_dev(b2lz4_ctx* c, const void* src, size_t n, uint32_t seed, uint32_t* out_dev, void* stream) {
     if (!c || !out_dev) return B2LZ4F_ERR_PARAMETER_NULL;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -828,6 +872,64 @@ static int host_batch(b2lz4_ctx* c, Op op, int param, const void* srcv, const ui
     return B2LZ4_OK;
 }
 
+// compressDestSize over host buffers: src_len[i] is the most block i may consume, dst_cap[i] the room it has.
+static int host_dest_size_batch(b2lz4_ctx* c, const void* srcv, const uint64_t* src_off, const uint32_t* src_len, void* dstv,
+                                const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* consumed, uint32_t* out_len,
+                                int32_t* status, size_t nb) {
+    if (!c) return B2LZ4F_ERR_PARAMETER_NULL;
+    if (nb == 0) return B2LZ4_OK;
+    if (nb > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
+    uint32_t max_len = 0;
+    for (size_t i = 0; i < nb; i++) {
+        s_lo = std::min(s_lo, src_off[i]); s_hi = std::max(s_hi, src_off[i] + src_len[i]);
+        d_lo = std::min(d_lo, dst_off[i]); d_hi = std::max(d_hi, dst_off[i] + dst_cap[i]);
+        max_len = std::max(max_len, src_len[i]);
+    }
+    const size_t s_span = (size_t)(s_hi - s_lo), d_span = (size_t)(d_hi - d_lo);
+    B2_CUDA(c->stage_in[0].ensure(s_span + 16));
+    B2_CUDA(c->stage_out[0].ensure(d_span + 16));
+    B2_CUDA(c->stage_aux.ensure(nb * (8 + 8 + 4 * 5) + 64));
+    uint64_t* d_soff = c->stage_aux.as<uint64_t>();
+    uint64_t* d_doff = d_soff + nb;
+    uint32_t* d_slen = (uint32_t*)(d_doff + nb);
+    uint32_t* d_dcap = d_slen + nb;
+    uint32_t* d_used = d_dcap + nb;
+    uint32_t* d_olen = d_used + nb;
+    int32_t* d_stat = (int32_t*)(d_olen + nb);
+    std::vector<uint64_t> so(nb), dofs(nb);
+    for (size_t i = 0; i < nb; i++) { so[i] = src_off[i] - s_lo; dofs[i] = dst_off[i] - d_lo; }
+    B2_CUDA(cudaMemcpyAsync(d_soff, so.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_doff, dofs.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_slen, src_len, nb * 4, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_dcap, dst_cap, nb * 4, cudaMemcpyHostToDevice, s));
+    if (s_span) B2_CUDA(cudaMemcpyAsync(c->stage_in[0].p, (const uint8_t*)srcv + s_lo, s_span, cudaMemcpyHostToDevice, s));
+    { int rc = dest_size_dev(c, c->stage_in[0].p, d_soff, d_slen, c->stage_out[0].p, d_doff, d_dcap, d_used, d_olen, d_stat, nb,
+                             max_len, s); if (rc) return rc; }
+    B2_CUDA(cudaMemcpyAsync(consumed, d_used, nb * 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(out_len, d_olen, nb * 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(status, d_stat, nb * 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if (nb <= 64) {
+        for (size_t i = 0; i < nb; i++)
+            if (status[i] == 0 && out_len[i])
+                B2_CUDA(cudaMemcpyAsync((uint8_t*)dstv + dst_off[i], c->stage_out[0].as<uint8_t>() + dofs[i], out_len[i],
+                                        cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+    } else {
+        B2_CUDA(c->pin_aux.ensure(d_span + 64));
+        B2_CUDA(cudaMemcpyAsync(c->pin_aux.p, c->stage_out[0].p, d_span, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        const uint8_t* t = c->pin_aux.as<uint8_t>();
+        for (size_t i = 0; i < nb; i++)
+            if (status[i] == 0 && out_len[i]) memcpy((uint8_t*)dstv + dst_off[i], t + dofs[i], out_len[i]);
+    }
+    return B2LZ4_OK;
+}
+
 static int host_single(Op op, int param, const void* src, size_t n, void* dst, size_t cap, const void* dict, size_t dict_len,
                        size_t* out) {
     if (!out) return B2LZ4F_ERR_PARAMETER_NULL;
@@ -865,6 +967,28 @@ int b2lz4_compress_hc_batch(b2lz4_ctx* c, const void* src, const uint64_t* so, c
     int nbs = hc_nb_searches(level);
     if (nbs < 0) return B2LZ4_ERR_UNSUPPORTED_LEVEL;
     return host_batch(c, Op::HC, nbs, src, so, sl, dst, dofs, dc, ol, st, nb, nullptr, 0);
+}
+
+int b2lz4_compress_dest_size_batch(b2lz4_ctx* c, const void* src, const uint64_t* so, const uint32_t* sl, void* dst,
+                                   const uint64_t* dofs, const uint32_t* dc, uint32_t* consumed, uint32_t* ol, int32_t* st,
+                                   size_t nb) {
+    return host_dest_size_batch(c, src, so, sl, dst, dofs, dc, consumed, ol, st, nb);
+}
+int b2lz4_compress_dest_size(const void* src, void* dst, size_t cap, size_t* src_size, size_t* out) {  // src/lz4.zig:551-616
+    if (!out || !src_size) return B2LZ4F_ERR_PARAMETER_NULL;
+    *out = 0;
+    const size_t max_len = *src_size;
+    if (max_len == 0) return B2LZ4_OK;                                  // :553-556 (*src_size stays 0)
+    if (max_len > LZ4_MAX_INPUT_SIZE) return B2LZ4_ERR_INPUT_TOO_LARGE;  // :559-561 -> :296; *src_size unchanged
+    b2lz4_ctx* c; int rc = b2_default_ctx(&c); if (rc) return rc;
+    uint64_t so = 0, dofs = 0;
+    uint32_t sl = (uint32_t)max_len, dc = (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFull), used = 0, ol = 0; int32_t st = 0;
+    rc = host_dest_size_batch(c, src, &so, &sl, dst, &dofs, &dc, &used, &ol, &st, 1);
+    if (rc) return rc;
+    if (st) return st;
+    *src_size = used;
+    *out = ol;
+    return B2LZ4_OK;
 }
 
 int b2lz4_compress_fast(const void* src, size_t n, void* dst, size_t cap, uint32_t accel, size_t* out) {

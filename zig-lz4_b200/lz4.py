@@ -62,6 +62,18 @@ def compressFastUsingDict(src, dict, acceleration=1, dst_capacity=None):
     return _call_out(lib().b2lz4_compress_fast_using_dict, src, cap, dp if dn else 0, dn, acceleration)
 
 
+def compressDestSize(src, dst_capacity, src_size=None):
+    """reference src/lz4.zig:551-616: compress the longest prefix of src[:src_size] the reference's bisection finds to
+    fit dst_capacity bytes.  Returns (compressed bytes, consumed) — the Zig call returns the size and updates
+    srcSizePtr.*."""
+    p, n, keep = as_buffer(src)
+    used = C.c_size_t(n if src_size is None else src_size)
+    dst = (C.c_uint8 * max(1, dst_capacity))()
+    out = C.c_size_t(0)
+    check(lib().b2lz4_compress_dest_size(p, dst, dst_capacity, C.byref(used), C.byref(out)))
+    return bytes(dst[:out.value]), used.value
+
+
 def decompressSafe(src, dst_capacity):
     """reference src/lz4.zig:257-259"""
     return _call_out(lib().b2lz4_decompress_safe, src, dst_capacity)

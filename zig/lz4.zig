@@ -27,6 +27,7 @@ const c = struct {
     pub extern "c" fn b2lz4_decompress_safe(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, out: *usize) c_int;
     pub extern "c" fn b2lz4_decompress_safe_using_dict(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, dict: [*]const u8, dict_len: usize, out: *usize) c_int;
     pub extern "c" fn b2lz4_compress_fast_using_dict(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, dict: [*]const u8, dict_len: usize, acceleration: u32, out: *usize) c_int;
+    pub extern "c" fn b2lz4_compress_dest_size(src: [*]const u8, dst: [*]u8, cap: usize, src_size: *usize, out: *usize) c_int;
     pub extern "c" fn b2lz4_compress_hc(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, level: c_int, out: *usize) c_int;
     pub extern "c" fn b2lz4f_compress_frame_bound(n: usize, prefs: ?*const Prefs) usize;
     pub extern "c" fn b2lz4f_compress_frame(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, prefs: ?*const Prefs, out: *usize) c_int;
@@ -76,6 +77,12 @@ pub const lz4 = struct {
     pub fn decompressSafeUsingDict(src: []const u8, dst: []u8, dict: []const u8) Error!usize {
         var out: usize = 0;
         try check(c.b2lz4_decompress_safe_using_dict(src.ptr, src.len, dst.ptr, dst.len, dict.ptr, dict.len, &out));
+        return out;
+    }
+    /// reference src/lz4.zig:551-616 (same consumed / compressed sizes; dst holds the stream of the consumed prefix)
+    pub fn compressDestSize(src: []const u8, dst: []u8, srcSizePtr: *usize) Error!usize {
+        var out: usize = 0;
+        try check(c.b2lz4_compress_dest_size(src.ptr, dst.ptr, dst.len, srcSizePtr, &out));
         return out;
     }
     /// Not in the reference: compressFast with the table primed by `dict` — the encode side of
