@@ -8,10 +8,17 @@
 // cannot be split or prefix-scanned.  So:
 //   * block checksums: ONE WARP PER BLOCK.  The 32 lanes stream the block through shared memory in 2 KiB
 //     tiles (coalesced 16-byte loads, the next tile in flight while this one is hashed); lanes 0..3 each
-//     run one accumulator chain at ~13 cycles per 16-byte stripe.  (A single thread per block — the first
-//     version — exposed one DRAM round trip per 64 bytes: 37 ms for 512 blocks of 4 MiB, now ~2 ms.)
+//     run one accumulator chain.  (A single thread per block — the first version — exposed one DRAM round
+//     trip per 64 bytes: 37 ms for 512 blocks of 4 MiB, now ~2 ms.)
 //   * content checksum: one warp; 32 lanes stream 2 KiB tiles into shared memory (double buffered),
-//     lanes 0..3 each run one accumulator chain.  ~14 cycles per 16-byte stripe, inherently.
+//     lanes 0..3 each run one accumulator chain.
+//   The chain itself is the bound, so it is written for dependent-issue latency (chain_tile below): the
+//   tile is stored one row per accumulator so a chain lane fetches four rounds of input per LDS.128, one
+//   group ahead; x*P2 is computed off the chain; and the round is rewritten from
+//   IMAD -> SHF(rotl) -> IMAD (three dependent ops) into b' = (b*C1 + y') + (b>>19)*P1 with b = acc + y,
+//   C1 = P1<<13 (rotl(b,13)*P1 = b*C1 + (b>>19)*P1 mod 2^32): IMAD || SHF, then one IMAD — two deep.
+//   Measured on one B200 warp (tools/exp/xxh_chain_bench.cu): 10.1 -> 7.3 ns per 16-byte stripe
+//   (1.59 -> 2.20 GB/s); the mul.hi form of b>>19 (all on the fma pipe) is slower (9.1 ns).
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 
@@ -38,9 +45,44 @@ __device__ __forceinline__ uint32_t xxh_finish(uint32_t h, const uint8_t* p, uin
 
 constexpr uint32_t TILE = 2048;  // bytes per shared-memory tile (128 stripes)
 constexpr int XXH_WARPS = 4;
+constexpr uint32_t ROW = 132;                 // words per accumulator row: 128 + 4 pad (the four chain lanes hit different banks)
+constexpr uint32_t TILE_WORDS = 4 * ROW;      // one staged tile: row j holds word j of every stripe
+constexpr uint32_t C1 = P1 << 13;
+
+// stripes held in registers (lane + 32u of the tile) -> rows of the staged tile
+__device__ __forceinline__ void stage_tile(uint32_t* tile, const uint4 (&r)[4], uint32_t cnt, uint32_t lane) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint32_t s = lane + 32u * u;
+        if (s < cnt) { uint32_t* t = tile + s; t[0] = r[u].x; t[ROW] = r[u].y; t[2 * ROW] = r[u].z; t[3 * ROW] = r[u].w; }
+    }
+}
+
+__device__ __forceinline__ uint32_t chain_step(uint32_t b, uint32_t ynext) { return (b >> 19) * P1 + (b * C1 + ynext); }
+
+// `cnt` rounds of one accumulator over its row of the staged tile
+__device__ __forceinline__ uint32_t chain_tile(uint32_t acc, const uint32_t* row, uint32_t cnt) {
+    if (cnt == 128) {
+        uint4 cur = *reinterpret_cast<const uint4*>(row);
+        uint32_t b = acc + cur.x * P2;
+#pragma unroll 4
+        for (uint32_t g = 0; g < 32; g++) {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (g + 1 < 32) nxt = *reinterpret_cast<const uint4*>(row + 4 * (g + 1));
+            b = chain_step(b, cur.y * P2);
+            b = chain_step(b, cur.z * P2);
+            b = chain_step(b, cur.w * P2);
+            b = chain_step(b, nxt.x * P2);   // after the last group y = 0: b is the accumulator again
+            cur = nxt;
+        }
+        return b;
+    }
+    for (uint32_t s = 0; s < cnt; s++) acc = xround(acc, row[s]);
+    return acc;
+}
 
 // XXH32 of [p, p + len) by one warp; `tile` is this warp's 2 x 2 KiB staging area.  Result in every lane.
-__device__ uint32_t xxh32_warp(const uint8_t* __restrict__ p, uint32_t len, uint32_t seed, uint32_t (*tile)[TILE / 4],
+__device__ uint32_t xxh32_warp(const uint8_t* __restrict__ p, uint32_t len, uint32_t seed, uint32_t (*tile)[TILE_WORDS],
                                uint32_t lane) {
     uint32_t acc = seed;
     if (lane == 0) acc = seed + P1 + P2;
@@ -65,18 +107,10 @@ __device__ uint32_t xxh32_warp(const uint8_t* __restrict__ p, uint32_t len, uint
     if (nst) load_tile(0);
     while (done < nst) {
         const uint32_t cnt = nst - done < 128 ? nst - done : 128;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t s = lane + 32u * u;
-            if (s < cnt) reinterpret_cast<uint4*>(tile[buf])[s] = r[u];
-        }
+        stage_tile(tile[buf], r, cnt, lane);
         __syncwarp();
         if (done + 128 < nst) load_tile(done + 128);  // next tile in flight while the chains run
-        if (lane < 4) {
-            const uint32_t* t = tile[buf] + lane;
-#pragma unroll 8
-            for (uint32_t s = 0; s < cnt; s++) acc = xround(acc, t[4 * s]);
-        }
+        if (lane < 4) acc = chain_tile(acc, tile[buf] + lane * ROW, cnt);
         done += cnt;
         buf ^= 1;
         __syncwarp();
@@ -90,7 +124,7 @@ __device__ uint32_t xxh32_warp(const uint8_t* __restrict__ p, uint32_t len, uint
 
 __global__ void __launch_bounds__(XXH_WARPS * 32) k_xxh32_stored(BlockSet slots, BlockSet raw, const uint32_t* __restrict__ csize,
                                                                 uint32_t* __restrict__ sums, uint32_t nblocks) {
-    __shared__ __align__(16) uint32_t tiles[XXH_WARPS][2][TILE / 4];
+    __shared__ __align__(16) uint32_t tiles[XXH_WARPS][2][TILE_WORDS];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * XXH_WARPS + w;
     if (i >= nblocks) return;
@@ -106,7 +140,7 @@ __global__ void __launch_bounds__(XXH_WARPS * 32) k_xxh32_stored(BlockSet slots,
 __global__ void __launch_bounds__(XXH_WARPS * 32) k_xxh32_ranges(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off,
                                                                 const uint32_t* __restrict__ hdr, uint32_t* __restrict__ sums,
                                                                 uint32_t nblocks) {
-    __shared__ __align__(16) uint32_t tiles[XXH_WARPS][2][TILE / 4];
+    __shared__ __align__(16) uint32_t tiles[XXH_WARPS][2][TILE_WORDS];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * XXH_WARPS + w;
     if (i >= nblocks) return;
@@ -139,7 +173,7 @@ __global__ void k_xxh32_init(XxhState* st, uint32_t seed) {
 
 // One warp.  Consumes n bytes at p, continuing from *st (src/lz4f.zig:385 XxHash32.update).
 __global__ void __launch_bounds__(32) k_xxh32_update(XxhState* st, const uint8_t* __restrict__ p, uint64_t n) {
-    __shared__ __align__(16) uint32_t tile[2][TILE / 4];
+    __shared__ __align__(16) uint32_t tile[2][TILE_WORDS];
     __shared__ uint8_t tailb[32];
     const uint32_t lane = threadIdx.x;
     uint32_t acc = lane < 4 ? st->v[lane] : 0;
@@ -185,18 +219,10 @@ __global__ void __launch_bounds__(32) k_xxh32_update(XxhState* st, const uint8_t
     if (nst) load_tile(0);
     while (done < nst) {
         uint32_t cnt = (uint32_t)(nst - done < 128 ? nst - done : 128);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            uint32_t s = lane + 32u * u;
-            if (s < cnt) reinterpret_cast<uint4*>(tile[buf])[s] = r[u];
-        }
+        stage_tile(tile[buf], r, cnt, lane);
         __syncwarp();
         if (done + 128 < nst) load_tile(done + 128);  // prefetch the next tile while the chains run
-        if (lane < 4) {
-            const uint32_t* t = tile[buf] + lane;
-#pragma unroll 8
-            for (uint32_t s = 0; s < cnt; s++) acc = xround(acc, t[4 * s]);
-        }
+        if (lane < 4) acc = chain_tile(acc, tile[buf] + lane * ROW, cnt);
         done += cnt;
         buf ^= 1;
     }
