@@ -198,7 +198,10 @@ def main():
     n = args.bytes
     bs = 65536
     zp = make_prefs_pair(n)
-    ctx = z.Context(local)
+    # N > 1: the frame is sharded by block range, one process per GPU (zig-lz4_b200/sharded.py)
+    from zig_lz4_b200 import sharded
+    engine = sharded.CudaEngine(local) if world > 1 else None
+    ctx = engine.ctx if engine else z.Context(local)
 
     # ---- synthetic shard of this rank (rank r holds blocks [r*B, (r+1)*B) of the world-sized frame) ----
     host = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -209,7 +212,6 @@ def main():
     back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     s = stream.cuda_stream
-    sizes_dev = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def step():
         """compress the shard, exchange body sizes (N>1), decompress it back.  Returns (csize, tc_ms, td_ms)."""
@@ -218,15 +220,15 @@ def main():
         if world == 1:
             csize = ctx.compress_frame_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, s)
         else:
-            csize = ctx.compress_blocks_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, s)
-            mine = torch.tensor([csize], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(sizes_dev, mine)          # per-GPU compressed-size offsets
+            # body of this rank's blocks + the one all_gather of body sizes that fixes the frame layout
+            _, layout, body = sharded.compress_frame_sharded(engine, src, zp, gather_to=None)
+            csize = body.numel()
         ph_c = ctx.last_phase_ms()
         e1.record(stream)
         if world == 1:
             m = ctx.decompress_frame_dev(comp.data_ptr(), csize, back.data_ptr(), n, s)
         else:
-            m = ctx.decompress_blocks_dev(comp.data_ptr(), csize, back.data_ptr(), n, bs, False, s)
+            m = ctx.decompress_blocks_dev(body.data_ptr(), csize, back.data_ptr(), n, bs, False, s)
         ph_d = ctx.last_phase_ms()
         e2.record(stream)
         e2.synchronize()

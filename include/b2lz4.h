@@ -244,6 +244,25 @@ B2LZ4_API int b2lz4f_compress_blocks_dev(b2lz4_ctx* ctx, const void* src, size_t
 /* Decode a body (device pointers); block_size in bytes; expects exactly the records, no end mark. */
 B2LZ4_API int b2lz4f_decompress_blocks_dev(b2lz4_ctx* ctx, const void* src, size_t n, void* dst, size_t cap,
                                            size_t block_size, int block_checksum, size_t* out, void* stream);
+/* Block index of a whole frame held in device memory — the header chain lz4f.decompressFrame walks serially
+ * (reference src/lz4f.zig:563-589), built by the parallel index kernels.  Parses the frame header (same errors
+ * as lz4f.parseFrameHeader), then writes for block i the position of its payload (off_dev[i], right after
+ * the 4-byte block header) and the header word (hdr_dev[i], bit 31 = stored raw) for up to `capacity` blocks
+ * (device arrays; may be NULL with capacity 0 to only count).  A multi-GPU decode splits the frame on these:
+ * blocks [b0, b1) are the body bytes [off[b0] - 4, off[b1] - 4), decodable with b2lz4f_decompress_blocks_dev. */
+typedef struct b2lz4f_frame_index {
+    uint64_t nblocks;         /* blocks on the chain */
+    uint64_t end_pos;         /* position after the end mark (where the content checksum sits, if any) */
+    uint64_t content_size;    /* from the header, 0 = absent */
+    uint32_t terminal;        /* 0 = end mark seen, 1 = ran off the end without one, 2 = truncated (FrameSizeWrong) */
+    uint32_t header_size;
+    uint32_t block_size;      /* bytes */
+    uint32_t block_checksum;  /* 0 / 1 */
+    uint32_t content_checksum;
+    uint32_t max_stored;      /* largest block payload */
+} b2lz4f_frame_index;
+B2LZ4_API int b2lz4f_index_frame_dev(b2lz4_ctx* ctx, const void* src, size_t n, uint64_t* off_dev, uint32_t* hdr_dev,
+                                     size_t capacity, b2lz4f_frame_index* info, void* stream);
 /* Running XXH32 state for the content checksum hand-off rank k -> k+1: 4 lanes, the
  * <16-byte tail, and the byte count — 40 bytes, plain data so it can be sent with any transport. */
 typedef struct b2lz4_xxh32_state {

@@ -42,6 +42,12 @@ class Prefs(C.Structure):
                 ("favor_dec_speed", C.c_uint32)]
 
 
+class XxhState(C.Structure):
+    """b2o_xxh32_state (b2o.h)"""
+    _fields_ = [("v", C.c_uint32 * 4), ("buf", C.c_uint8 * 16), ("buf_len", C.c_uint32), ("total", C.c_uint64),
+                ("seed", C.c_uint32)]
+
+
 def build(force=False):
     if force or not os.path.exists(_SO) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
@@ -69,6 +75,12 @@ def lib():
         L.b2o_hc_f8_guard_hits.restype = C.c_uint64
         L.b2o_xxh32.restype = C.c_uint32
         L.b2o_xxh32.argtypes = [u8p, sz, C.c_uint32]
+        L.b2o_xxh32_init.restype = None
+        L.b2o_xxh32_init.argtypes = [C.POINTER(XxhState), C.c_uint32]
+        L.b2o_xxh32_update.restype = None
+        L.b2o_xxh32_update.argtypes = [C.POINTER(XxhState), u8p, sz]
+        L.b2o_xxh32_final.restype = C.c_uint32
+        L.b2o_xxh32_final.argtypes = [C.POINTER(XxhState)]
         L.b2o_compress_frame_bound.restype = sz
         L.b2o_compress_frame_bound.argtypes = [sz, C.POINTER(Prefs)]
         L.b2o_compress_frame.argtypes = [u8p, sz, u8p, sz, C.POINTER(Prefs), szp]
@@ -158,6 +170,23 @@ def compress_hc(src, level=9, cap=None):
 def xxh32(data, seed=0):
     p, n, keep = _buf(data)
     return lib().b2o_xxh32(p, n, seed)
+
+
+def xxh32_state_init(seed=0):
+    st = XxhState()
+    lib().b2o_xxh32_init(C.byref(st), seed)
+    return st
+
+
+def xxh32_state_update(st, data):
+    p, n, keep = _buf(data)
+    if n:
+        lib().b2o_xxh32_update(C.byref(st), p, n)
+    return st
+
+
+def xxh32_state_final(st):
+    return lib().b2o_xxh32_final(C.byref(st))
 
 
 def make_prefs(block_size_id=0, block_mode=0, content_checksum=0, content_size=0, dict_id=0, block_checksum=0,

@@ -55,6 +55,13 @@ class XxhState(C.Structure):
                 ("total", C.c_uint64)]
 
 
+class FrameIndex(C.Structure):
+    """struct b2lz4f_frame_index (include/b2lz4.h)"""
+    _fields_ = [("nblocks", C.c_uint64), ("end_pos", C.c_uint64), ("content_size", C.c_uint64), ("terminal", C.c_uint32),
+                ("header_size", C.c_uint32), ("block_size", C.c_uint32), ("block_checksum", C.c_uint32),
+                ("content_checksum", C.c_uint32), ("max_stored", C.c_uint32)]
+
+
 def library_path():
     return _SO
 
@@ -85,6 +92,7 @@ EXPORTS = [
     "b2lz4_compress_fast_batch", "b2lz4_decompress_safe_batch", "b2lz4_compress_hc_batch", "b2lz4_xxh32_dev",
     "b2lz4_compress_fast_using_dict", "b2lz4_compress_fast_dict_batch", "b2lz4_compress_fast_dict_batch_dev",
     "b2lz4_compress_dest_size", "b2lz4_compress_dest_size_batch", "b2lz4_compress_dest_size_batch_dev",
+    "b2lz4f_index_frame_dev",
     "b2lz4f_prefs_init", "b2lz4f_compress_frame_bound", "b2lz4f_compress_frame", "b2lz4f_decompress_frame",
     "b2lz4f_header_size", "b2lz4f_write_frame_header", "b2lz4f_parse_frame_header",
     "b2lz4f_compress_frame_ctx", "b2lz4f_decompress_frame_ctx", "b2lz4f_compress_frame_dev",
@@ -158,6 +166,7 @@ def lib():
     L.b2lz4f_decompress_frame_dev.argtypes = [vp, vp, sz, vp, sz, szp, vp]
     L.b2lz4f_compress_blocks_dev.argtypes = [vp, vp, sz, vp, sz, pp, szp, vp]
     L.b2lz4f_decompress_blocks_dev.argtypes = [vp, vp, sz, vp, sz, sz, i32, szp, vp]
+    L.b2lz4f_index_frame_dev.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(FrameIndex), vp]
     L.b2lz4_xxh32_state_init.argtypes = [C.POINTER(XxhState), u32]
     L.b2lz4_xxh32_state_init.restype = None
     L.b2lz4_xxh32_state_update_dev.argtypes = [vp, C.POINTER(XxhState), vp, sz, vp]
@@ -263,6 +272,16 @@ class Context:
         check(lib().b2lz4f_decompress_blocks_dev(self._h, src_ptr, n, dst_ptr, cap, block_size,
                                                   1 if block_checksum else 0, C.byref(out), stream))
         return out.value
+
+    def index_frame_dev(self, src_ptr, n, off_ptr=0, hdr_ptr=0, capacity=0, stream=0):
+        """block index of a frame in device memory -> FrameIndex; off/hdr device arrays are optional"""
+        info = FrameIndex()
+        check(lib().b2lz4f_index_frame_dev(self._h, src_ptr, n, off_ptr, hdr_ptr, capacity, C.byref(info), stream))
+        return info
+
+    def xxh32_state_update_dev(self, state, src_ptr, n, stream=0):
+        check(lib().b2lz4_xxh32_state_update_dev(self._h, C.byref(state), src_ptr, n, stream))
+        return state
 
     # ---- host-pointer frame codec with this context ----
     def compress_frame(self, src, prefs=None, cap=None, dst=None):

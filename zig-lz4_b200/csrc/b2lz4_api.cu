@@ -670,6 +670,38 @@ int b2lz4f_decompress_blocks_dev(b2lz4_ctx* c, const void* srcv, size_t n, void*
     return B2LZ4_OK;
 }
 
+int b2lz4f_index_frame_dev(b2lz4_ctx* c, const void* srcv, size_t n, uint64_t* off_dev, uint32_t* hdr_dev, size_t capacity,
+                           b2lz4f_frame_index* info, void* stream) {
+    if (!c || !info) return B2LZ4F_ERR_PARAMETER_NULL;
+    memset(info, 0, sizeof *info);
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    B2_CUDA(cudaSetDevice(c->device));
+    const uint8_t* src = (const uint8_t*)srcv;
+    uint8_t hb[32];
+    const size_t hn = n < 19 ? n : 19;
+    B2_CUDA(c->pin_aux.ensure(64));
+    if (hn) {
+        B2_CUDA(cudaMemcpyAsync(c->pin_aux.p, src, hn, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        memcpy(hb, c->pin_aux.p, hn);
+    }
+    b2lz4f_prefs fi; size_t hsize = 0;
+    int rc = b2lz4f_parse_frame_header(hb, hn, &fi, &hsize);
+    if (rc) return rc;
+    size_t bs; block_size_of(fi.block_size_id, bs);
+    WalkResult w;
+    rc = build_block_index(c, src, n, hsize, (uint32_t)bs, fi.block_checksum == 1, s, &w);
+    if (rc) return rc;
+    info->nblocks = w.nblocks; info->end_pos = w.end_pos; info->content_size = fi.content_size; info->terminal = w.terminal;
+    info->header_size = (uint32_t)hsize; info->block_size = (uint32_t)bs; info->block_checksum = fi.block_checksum == 1;
+    info->content_checksum = fi.content_checksum == 1; info->max_stored = w.max_stored;
+    const size_t take = std::min<size_t>(capacity, w.nblocks);
+    if (take && off_dev) B2_CUDA(cudaMemcpyAsync(off_dev, c->walk_off.p, take * 8, cudaMemcpyDeviceToDevice, s));
+    if (take && hdr_dev) B2_CUDA(cudaMemcpyAsync(hdr_dev, c->walk_hdr.p, take * 4, cudaMemcpyDeviceToDevice, s));
+    return B2LZ4_OK;
+}
+
 // ================================================================ batch API (device pointers)
 int b2lz4_compress_fast_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* src_off, const uint32_t* src_len, void* dst,
                                   const uint64_t* dst_off, const uint32_t* dst_cap, uint32_t* out_len, int32_t* status,
