@@ -385,3 +385,43 @@ def test_pipelined_host_decode_falls_back_exactly(z, oracle, small_pipeline_chun
             frame += (len(pt) | 0x80000000).to_bytes(4, "little") + pt
     frame += b"\0\0\0\0"
     assert _same_frame_result(z, oracle, bytes(frame), 5 << 20) == 0
+
+
+def test_calls_from_several_host_threads(z, oracle):
+    """SURVEY §8b threading: every entry point is callable from several host threads at once — on the shared default
+    context (calls serialise on its lock) and on one context per thread (calls overlap on the device)."""
+    import threading
+    from zig_lz4_b200 import datagen
+    inputs = [datagen.generate(300000 + 7919 * i, mode=i % 4, seed=40 + i).tobytes() for i in range(6)]
+    wants = [oracle.compress_frame(d, None) for d in inputs]
+    errors = []
+
+    def shared(i):
+        try:
+            for _ in range(3):
+                f = z.lz4f.compressFrame(inputs[i])
+                assert f == wants[i]
+                assert z.lz4f.decompressFrame(f, len(inputs[i])) == inputs[i]
+                b = inputs[i][:50000]
+                assert z.lz4.decompressSafe(z.lz4.compressDefault(b), len(b)) == b
+        except BaseException as e:          # noqa: surfaced below
+            errors.append(("shared", i, repr(e)))
+
+    def own(i):
+        try:
+            c = z.Context(0)
+            for _ in range(3):
+                f = c.compress_frame(inputs[i])
+                assert f == wants[i]
+                assert c.decompress_frame(f, cap=len(inputs[i])) == inputs[i]
+            c.close()
+        except BaseException as e:          # noqa
+            errors.append(("own", i, repr(e)))
+
+    threads = [threading.Thread(target=shared, args=(i,)) for i in range(6)] + [threading.Thread(target=own, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads)
