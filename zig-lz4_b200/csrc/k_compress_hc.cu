@@ -30,7 +30,12 @@
 namespace b2 {
 
 constexpr int HC_WARPS = 4;                 // warps per CTA
-constexpr int HC_CTAS_PER_SM = 8;     // 32 warps per SM: the chain walk is an L2 pointer chase, more blocks in flight = more throughput
+// K3 is bound by the latency of its dependent table reads, so blocks per second grow with the warps in flight
+// (5.7k / 7.9k / 9.7k blocks/s at 32 / 48 / 64 warps per SM on 4 GiB of text).  64 warps per SM leave 32 registers per
+// thread (a few spills, each block ~5 % slower), which only pays when there are more blocks than the 32-warp variant
+// holds at once: the launcher picks.
+constexpr int HC_CTAS_PER_SM = 16;          // workspace is sized for the 64-warp variant
+constexpr int HC_CTAS_PER_SM_FEW = 8;       // 32 warps per SM, 56 registers, no spills
 constexpr uint32_t HC_HASH = 32768, HC_CHAIN = 65536;
 
 struct HcWork {
@@ -253,7 +258,8 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     olen = op;
 }
 
-__global__ void __launch_bounds__(HC_WARPS * 32) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
+template <int CTAS>
+__global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                                int32_t* __restrict__ status, uint32_t nblocks, int nbs,
                                                                HcWork* work, uint32_t* ticket) {
     const uint32_t lane = lane_id();
@@ -280,11 +286,16 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     if (nblocks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    uint32_t maxg = (uint32_t)(num_sms * HC_CTAS_PER_SM);
-    uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
-    uint32_t grid = want < maxg ? want : maxg;
-    k_compress_hc<<<grid, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
-                                                      reinterpret_cast<HcWork*>(work), ticket);
+    const uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
+    const uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
+    if (want <= few) {
+        k_compress_hc<HC_CTAS_PER_SM_FEW><<<want, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
+                                                                              reinterpret_cast<HcWork*>(work), ticket);
+    } else {
+        const uint32_t maxg = (uint32_t)(num_sms * HC_CTAS_PER_SM);
+        k_compress_hc<HC_CTAS_PER_SM><<<want < maxg ? want : maxg, HC_WARPS * 32, 0, stream>>>(
+            in, out, out_len, status, nblocks, nb_searches, reinterpret_cast<HcWork*>(work), ticket);
+    }
     count_launch();
     return cudaGetLastError();
 }
