@@ -263,6 +263,14 @@ typedef struct b2lz4f_frame_index {
 } b2lz4f_frame_index;
 B2LZ4_API int b2lz4f_index_frame_dev(b2lz4_ctx* ctx, const void* src, size_t n, uint64_t* off_dev, uint32_t* hdr_dev,
                                      size_t capacity, b2lz4f_frame_index* info, void* stream);
+/* One process, several GPUs (SURVEY section 8b "multi-GPU variants taking ngpus"): lz4f.compressFrame /
+ * lz4f.decompressFrame on host slices with the frame sharded by contiguous block range over devices 0..ngpus-1
+ * (clamped to the devices present), one host thread and one context per device inside the call, each range on its
+ * own GPU's PCIe link.  Same bytes, sizes and errors as the one-GPU calls; frames with fewer than 4 blocks per GPU,
+ * foreign layouts and every error case run on one GPU. */
+B2LZ4_API int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,
+                                         int ngpus, size_t* out);
+B2LZ4_API int b2lz4f_decompress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap, int ngpus, size_t* out);
 /* Running XXH32 state for the content checksum hand-off rank k -> k+1: 4 lanes, the
  * <16-byte tail, and the byte count — 40 bytes, plain data so it can be sent with any transport. */
 typedef struct b2lz4_xxh32_state {

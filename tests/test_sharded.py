@@ -87,3 +87,65 @@ def test_cuda_engine_single_rank(z, oracle):
             with pytest.raises(z.B2Error) as e:
                 sharded.decompress_frame_sharded(eng, bad)
             assert e.value.name == "lz4f.ContentChecksumInvalid"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bsid,bc,cc", [(4, 1, 1), (4, 0, 0), (5, 1, 0)])
+def test_single_process_multi_gpu_calls(z, oracle, bsid, bc, cc):
+    """b2lz4f_compress_frame_mgpu / _decompress_frame_mgpu: same bytes, sizes and errors as the one-GPU calls, for any
+    ngpus (clamped to the devices present: on a one-GPU box this runs the one-GPU path, on a multi-GPU box the sharded one)"""
+    import torch
+    from zig_lz4_b200 import datagen
+    n = (24 << 20) + 777
+    data = datagen.generate(n, mode=4, seed=9).tobytes()
+    prefs = z.lz4f.Preferences(blockSizeID=bsid, blockMode=1, blockChecksumFlag=bc, contentChecksumFlag=cc, contentSize=n)
+    want = oracle.compress_frame(data, oracle.make_prefs(bsid, 1, cc, n, 0, bc, 0), threads=8)
+    for ngpus in (1, 2, 8):
+        f = z.lz4f.compressFrameMultiGPU(data, prefs, ngpus=ngpus)
+        assert f == want, (ngpus, len(f), len(want))
+        assert z.lz4f.decompressFrameMultiGPU(f, n, ngpus=ngpus) == data
+        assert z.lz4f.decompressFrameMultiGPU(f, n + 1000, ngpus=ngpus) == data
+    ngpus = max(2, torch.cuda.device_count())
+    # errors keep the one-GPU kinds
+    with pytest.raises(z.B2Error) as e:
+        z.lz4f.decompressFrameMultiGPU(want, n - 1, ngpus=ngpus)
+    assert e.value.name == _one_gpu_error(z, want, n - 1)
+    bad = bytearray(want)
+    bad[len(bad) // 2] ^= 0x40
+    assert _mgpu_result(z, bytes(bad), n, ngpus) == _one_gpu_result(z, bytes(bad), n)
+    if cc:
+        bad = bytearray(want)
+        bad[-1] ^= 1
+        with pytest.raises(z.B2Error) as e:
+            z.lz4f.decompressFrameMultiGPU(bytes(bad), n, ngpus=ngpus)
+        assert e.value.name == "lz4f.ContentChecksumInvalid"
+    with pytest.raises(z.B2Error) as e:
+        z.lz4f.compressFrameMultiGPU(data, prefs, ngpus=ngpus, dst=bytearray(len(want)))
+    assert e.value.name == "lz4f.DstMaxSizeTooSmall"
+    # short frames and empty input take the one-GPU path
+    small = data[:100000]
+    sp = z.lz4f.Preferences(blockSizeID=bsid, blockMode=1, blockChecksumFlag=bc, contentChecksumFlag=cc)
+    assert z.lz4f.compressFrameMultiGPU(small, sp, ngpus=ngpus) == z.lz4f.compressFrame(small, sp)
+    assert z.lz4f.compressFrameMultiGPU(b"", sp, ngpus=ngpus) == z.lz4f.compressFrame(b"", sp)
+
+
+def _one_gpu_result(z, frame, cap):
+    try:
+        return (0, z.lz4f.decompressFrame(frame, cap))
+    except z.B2Error as e:
+        return (e.code, None)
+
+
+def _mgpu_result(z, frame, cap, ngpus):
+    try:
+        return (0, z.lz4f.decompressFrameMultiGPU(frame, cap, ngpus=ngpus))
+    except z.B2Error as e:
+        return (e.code, None)
+
+
+def _one_gpu_error(z, frame, cap):
+    try:
+        z.lz4f.decompressFrame(frame, cap)
+    except z.B2Error as e:
+        return e.name
+    return "ok"

@@ -92,7 +92,7 @@ EXPORTS = [
     "b2lz4_compress_fast_batch", "b2lz4_decompress_safe_batch", "b2lz4_compress_hc_batch", "b2lz4_xxh32_dev",
     "b2lz4_compress_fast_using_dict", "b2lz4_compress_fast_dict_batch", "b2lz4_compress_fast_dict_batch_dev",
     "b2lz4_compress_dest_size", "b2lz4_compress_dest_size_batch", "b2lz4_compress_dest_size_batch_dev",
-    "b2lz4f_index_frame_dev",
+    "b2lz4f_index_frame_dev", "b2lz4f_compress_frame_mgpu", "b2lz4f_decompress_frame_mgpu",
     "b2lz4f_prefs_init", "b2lz4f_compress_frame_bound", "b2lz4f_compress_frame", "b2lz4f_decompress_frame",
     "b2lz4f_header_size", "b2lz4f_write_frame_header", "b2lz4f_parse_frame_header",
     "b2lz4f_compress_frame_ctx", "b2lz4f_decompress_frame_ctx", "b2lz4f_compress_frame_dev",
@@ -166,6 +166,8 @@ def lib():
     L.b2lz4f_decompress_frame_dev.argtypes = [vp, vp, sz, vp, sz, szp, vp]
     L.b2lz4f_compress_blocks_dev.argtypes = [vp, vp, sz, vp, sz, pp, szp, vp]
     L.b2lz4f_decompress_blocks_dev.argtypes = [vp, vp, sz, vp, sz, sz, i32, szp, vp]
+    L.b2lz4f_compress_frame_mgpu.argtypes = [vp, sz, vp, sz, pp, i32, szp]
+    L.b2lz4f_decompress_frame_mgpu.argtypes = [vp, sz, vp, sz, i32, szp]
     L.b2lz4f_index_frame_dev.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(FrameIndex), vp]
     L.b2lz4_xxh32_state_init.argtypes = [C.POINTER(XxhState), u32]
     L.b2lz4_xxh32_state_init.restype = None

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <new>
+#include <thread>
 #include <vector>
 #include "b2_host.h"
 
@@ -398,6 +399,205 @@ int b2lz4f_compress_frame(const void* src, size_t n, void* dst, size_t cap, cons
 int b2lz4f_decompress_frame(const void* src, size_t n, void* dst, size_t cap, size_t* out) {
     b2lz4_ctx* c; int rc = b2_default_ctx(&c); if (rc) return rc;
     return b2lz4f_decompress_frame_ctx(c, src, n, dst, cap, out);
+}
+
+}  // extern "C"
+
+// ================================================================ one process, several GPUs
+// SURVEY §8b asks for "multi-GPU variants taking ngpus": the same host-slice calls, the frame sharded by contiguous
+// block range over devices 0..ngpus-1 (§8e), one host thread and one context per device, each range moving over its
+// own GPU's PCIe link.  Sizes of the compressed ranges are only known after the codec has run, so compression is two
+// phases (upload + codec on every GPU, then download of every body to its final offset); decoding knows every offset
+// in advance.  Anything unusual (short frame, foreign layout, any error) takes the single-GPU path, which is exact
+// in every corner.
+namespace {
+
+std::mutex g_mgpu_mu;
+std::vector<b2lz4_ctx*> g_mgpu_ctx;   // one context per device, created on first use, kept for the process
+
+static int mgpu_ctx(int dev, b2lz4_ctx** out) {
+    std::lock_guard<std::mutex> lk(g_mgpu_mu);
+    if ((int)g_mgpu_ctx.size() <= dev) g_mgpu_ctx.resize(dev + 1, nullptr);
+    if (!g_mgpu_ctx[dev]) { int rc = b2lz4_ctx_create(dev, &g_mgpu_ctx[dev]); if (rc) return rc; }
+    *out = g_mgpu_ctx[dev];
+    return B2LZ4_OK;
+}
+
+static int mgpu_count(int ngpus) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return 0;
+    return std::max(1, std::min(ngpus, count));
+}
+
+struct MgpuJob {
+    int dev = 0;
+    b2lz4_ctx* c = nullptr;
+    size_t in_lo = 0, in_len = 0;     // bytes of the caller's source this device reads
+    size_t out_off = 0, out_cap = 0;  // where its result goes / how much room it has
+    size_t produced = 0;
+    size_t blocks = 0;
+    int rc = B2LZ4_OK;
+};
+
+template <typename F>
+static void mgpu_run(std::vector<MgpuJob>& jobs, F fn) {
+    std::vector<std::thread> th;
+    th.reserve(jobs.size());
+    for (auto& j : jobs) th.emplace_back([&j, fn]() { j.rc = fn(j); });
+    for (auto& t : th) t.join();
+}
+
+static int first_error(const std::vector<MgpuJob>& jobs) {
+    for (const auto& j : jobs) if (j.rc) return j.rc;
+    return B2LZ4_OK;
+}
+
+// content checksum over the device-resident ranges, in order (one serial chain)
+static int mgpu_content_sum(std::vector<MgpuJob>& jobs, bool over_output, uint32_t* sum) {
+    b2lz4_xxh32_state st;
+    b2lz4_xxh32_state_init(&st, 0);
+    for (auto& j : jobs) {
+        const size_t len = over_output ? j.produced : j.in_len;
+        if (!len) continue;
+        const void* p = over_output ? j.c->stage_out[0].p : j.c->stage_in[0].p;
+        int rc = b2lz4_xxh32_state_update_dev(j.c, &st, p, len, nullptr);
+        if (rc) return rc;
+    }
+    *sum = b2lz4_xxh32_state_final(&st);
+    return B2LZ4_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs, int ngpus,
+                               size_t* out) {
+    if (!out) return B2LZ4F_ERR_PARAMETER_NULL;
+    *out = 0;
+    b2lz4f_prefs d; if (!prefs) { b2lz4f_prefs_init(&d); prefs = &d; }
+    const int G = mgpu_count(ngpus);
+    size_t bs;
+    if (G <= 1 || !block_size_of(prefs->block_size_id, bs) || (prefs->compression_level > 0 && !b2_hc_supported(prefs->compression_level)))
+        return b2lz4f_compress_frame(src, n, dst, cap, prefs, out);
+    const size_t nb = (n + bs - 1) / bs;
+    if (nb < (size_t)(4 * G)) return b2lz4f_compress_frame(src, n, dst, cap, prefs, out);
+    const size_t bound = b2lz4f_compress_frame_bound(n, prefs);
+    if (cap < bound) return B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL;   // src/lz4f.zig:363-366
+    const bool bc = prefs->block_checksum == 1, cc = prefs->content_checksum == 1;
+    size_t hsize = 0;
+    { int rc = b2lz4f_write_frame_header(dst, cap, prefs, &hsize); if (rc) return rc; }      // :369
+    std::vector<MgpuJob> jobs(G);
+    for (int g = 0; g < G; g++) {
+        const size_t b0 = (size_t)g * nb / G, b1 = (size_t)(g + 1) * nb / G;
+        jobs[g].dev = g;
+        jobs[g].in_lo = b0 * bs;
+        jobs[g].in_len = std::min(b1 * bs, n) - b0 * bs;
+        jobs[g].blocks = b1 - b0;
+        jobs[g].out_cap = (b1 - b0) * (4 + compress_bound(bs) + (bc ? 4 : 0));
+    }
+    // phase 1: upload + codec; every body stays on its device
+    mgpu_run(jobs, [&](MgpuJob& j) -> int {
+        int rc = mgpu_ctx(j.dev, &j.c); if (rc) return rc;
+        b2lz4_ctx* c = j.c;
+        std::lock_guard<std::recursive_mutex> lk(c->mu);
+        B2_CUDA(cudaSetDevice(c->device));
+        B2_CUDA(c->stage_in[0].ensure(j.in_len + 16));
+        B2_CUDA(c->stage_out[0].ensure(j.out_cap + 16));
+        rc = upload(c, c->stage_in[0].p, (const uint8_t*)src + j.in_lo, j.in_len, c->stream); if (rc) return rc;
+        rc = b2_compress_dev_impl(c, c->stage_in[0].p, j.in_len, c->stage_out[0].p, j.out_cap, prefs, &j.produced, c->stream, true);
+        if (rc) return rc;
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        return B2LZ4_OK;
+    });
+    { int rc = first_error(jobs); if (rc) return rc; }
+    size_t pos = hsize;
+    for (auto& j : jobs) { j.out_off = pos; pos += j.produced; }
+    uint32_t csum = 0;
+    if (cc) { int rc = mgpu_content_sum(jobs, false, &csum); if (rc) return rc; }
+    // phase 2: every body to its place in the frame
+    mgpu_run(jobs, [&](MgpuJob& j) -> int {
+        b2lz4_ctx* c = j.c;
+        std::lock_guard<std::recursive_mutex> lk(c->mu);
+        B2_CUDA(cudaSetDevice(c->device));
+        int rc = download(c, (uint8_t*)dst + j.out_off, c->stage_out[0].p, j.produced, c->stream); if (rc) return rc;
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        return B2LZ4_OK;
+    });
+    { int rc = first_error(jobs); if (rc) return rc; }
+    uint8_t* o = (uint8_t*)dst + pos;
+    o[0] = o[1] = o[2] = o[3] = 0;                                                            // end mark, :433
+    pos += 4;
+    if (cc) { o[4] = (uint8_t)csum; o[5] = (uint8_t)(csum >> 8); o[6] = (uint8_t)(csum >> 16); o[7] = (uint8_t)(csum >> 24); pos += 4; }
+    *out = pos;
+    return B2LZ4_OK;
+}
+
+int b2lz4f_decompress_frame_mgpu(const void* srcv, size_t n, void* dst, size_t cap, int ngpus, size_t* out) {
+    if (!out) return B2LZ4F_ERR_PARAMETER_NULL;
+    *out = 0;
+    const uint8_t* src = (const uint8_t*)srcv;
+    const int G = mgpu_count(ngpus);
+    auto single = [&]() { *out = 0; return b2lz4f_decompress_frame(srcv, n, dst, cap, out); };
+    if (G <= 1 || !src || !dst) return single();
+    b2lz4f_prefs info; size_t hsize = 0;
+    if (b2lz4f_parse_frame_header(src, n, &info, &hsize) != B2LZ4_OK) return single();
+    size_t bs; if (!block_size_of(info.block_size_id, bs)) return single();
+    const bool bc = info.block_checksum == 1, cc = info.content_checksum == 1;
+    const size_t tr = bc ? 4 : 0;
+    // the header chain, read from the caller's frame (src/lz4f.zig:563-591)
+    std::vector<uint64_t> off;
+    size_t p = hsize, end_mark_pos = 0;
+    bool end_mark = false;
+    while (p < n) {
+        if (p + 4 > n) return single();
+        const uint32_t h = rd32(src + p);
+        if (h == 0) { end_mark = true; end_mark_pos = p; p += 4; break; }
+        p += 4;
+        const size_t sz = h & 0x7FFFFFFFu;
+        if (p + sz + tr > n || sz > bs) return single();
+        off.push_back(p);
+        p += sz + tr;
+    }
+    const size_t nb = off.size();
+    if (!end_mark || nb < (size_t)(4 * G) || (cc && p + 4 > n)) return single();
+    if (cap < (nb - 1) * bs + 1) return single();
+    std::vector<MgpuJob> jobs(G);
+    for (int g = 0; g < G; g++) {
+        const size_t b0 = (size_t)g * nb / G, b1 = (size_t)(g + 1) * nb / G;
+        jobs[g].dev = g;
+        jobs[g].in_lo = off[b0] - 4;
+        jobs[g].in_len = (b1 < nb ? off[b1] - 4 : end_mark_pos) - jobs[g].in_lo;
+        jobs[g].blocks = b1 - b0;
+        jobs[g].out_off = b0 * bs;
+        jobs[g].out_cap = std::min((b1 - b0) * bs, cap - b0 * bs);
+    }
+    mgpu_run(jobs, [&](MgpuJob& j) -> int {
+        int rc = mgpu_ctx(j.dev, &j.c); if (rc) return rc;
+        b2lz4_ctx* c = j.c;
+        std::lock_guard<std::recursive_mutex> lk(c->mu);
+        B2_CUDA(cudaSetDevice(c->device));
+        B2_CUDA(c->stage_in[0].ensure(j.in_len + 32));
+        B2_CUDA(c->stage_out[0].ensure(j.out_cap + 16));
+        rc = upload(c, c->stage_in[0].p, src + j.in_lo, j.in_len, c->stream); if (rc) return rc;
+        rc = b2lz4f_decompress_blocks_dev(c, c->stage_in[0].p, j.in_len, c->stage_out[0].p, j.out_cap, bs, bc ? 1 : 0, &j.produced,
+                                          c->stream);
+        if (rc) return rc;
+        // every range but the last must fill its blocks exactly for the offsets to hold; the caller checks
+        rc = download(c, (uint8_t*)dst + j.out_off, c->stage_out[0].p, j.produced, c->stream); if (rc) return rc;
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        return B2LZ4_OK;
+    });
+    bool usual = first_error(jobs) == B2LZ4_OK;
+    for (int g = 0; usual && g + 1 < G; g++) usual = jobs[g].produced == jobs[g].blocks * bs;
+    if (!usual) return single();   // exact error kind / foreign layout: the serial-order semantics of the one-GPU path
+    if (cc) {                      // src/lz4f.zig:625-635
+        uint32_t csum = 0;
+        int rc = mgpu_content_sum(jobs, true, &csum); if (rc) return rc;
+        if (rd32(src + p) != csum) return B2LZ4F_ERR_CONTENT_CHECKSUM_INVALID;
+    }
+    *out = jobs[G - 1].out_off + jobs[G - 1].produced;
+    return B2LZ4_OK;
 }
 
 }  // extern "C"

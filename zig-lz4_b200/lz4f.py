@@ -82,6 +82,43 @@ def decompressFrame(src, dst_capacity):
     return bytes(buf[:out.value])
 
 
+def compressFrameMultiGPU(src, prefs=None, ngpus=8, dst=None):
+    """lz4f.compressFrame with the frame sharded over `ngpus` devices inside the call (b2lz4f_compress_frame_mgpu);
+    same bytes as compressFrame.  dst: optional writable buffer (e.g. pinned numpy array) -> returns the size."""
+    p, n, keep = as_buffer(src)
+    if dst is None:
+        cap = compressFrameBound(n, prefs)
+        buf = bytearray(cap)
+        dp, dn, dkeep = as_buffer(buf)
+    else:
+        dp, cap, dkeep = as_buffer(dst)
+        buf = None
+    out = C.c_size_t(0)
+    check(lib().b2lz4f_compress_frame_mgpu(p, n, dp, cap, _pp(prefs), ngpus, C.byref(out)))
+    if buf is None:
+        return out.value
+    del dkeep
+    return bytes(buf[:out.value])
+
+
+def decompressFrameMultiGPU(src, dst_capacity=None, ngpus=8, dst=None):
+    """lz4f.decompressFrame over `ngpus` devices (b2lz4f_decompress_frame_mgpu)"""
+    p, n, keep = as_buffer(src)
+    if dst is None:
+        buf = bytearray(dst_capacity)
+        dp, dn, dkeep = as_buffer(buf) if dst_capacity else (0, 0, None)
+        cap = dst_capacity
+    else:
+        dp, cap, dkeep = as_buffer(dst)
+        buf = None
+    out = C.c_size_t(0)
+    check(lib().b2lz4f_decompress_frame_mgpu(p, n, dp, cap, ngpus, C.byref(out)))
+    if buf is None:
+        return out.value
+    del dkeep
+    return bytes(buf[:out.value])
+
+
 def headerSize(src):
     """reference src/lz4f.zig:451-480"""
     p, n, keep = as_buffer(src)

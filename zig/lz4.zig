@@ -32,6 +32,8 @@ const c = struct {
     pub extern "c" fn b2lz4f_compress_frame_bound(n: usize, prefs: ?*const Prefs) usize;
     pub extern "c" fn b2lz4f_compress_frame(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, prefs: ?*const Prefs, out: *usize) c_int;
     pub extern "c" fn b2lz4f_decompress_frame(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, out: *usize) c_int;
+    pub extern "c" fn b2lz4f_compress_frame_mgpu(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, prefs: ?*const Prefs, ngpus: c_int, out: *usize) c_int;
+    pub extern "c" fn b2lz4f_decompress_frame_mgpu(src: [*]const u8, n: usize, dst: [*]u8, cap: usize, ngpus: c_int, out: *usize) c_int;
     pub extern "c" fn b2lz4f_header_size(src: [*]const u8, n: usize, out: *usize) c_int;
     pub extern "c" fn b2lz4f_create_compression_context(out: *?*anyopaque) c_int;
     pub extern "c" fn b2lz4f_free_compression_context(cctx: ?*anyopaque) void;
@@ -187,6 +189,18 @@ pub const lz4f = struct {
         _ = allocator;
         var out: usize = 0;
         try check(c.b2lz4f_decompress_frame(src.ptr, src.len, dst.ptr, dst.len, &out));
+        return out;
+    }
+    /// compressFrame / decompressFrame with the frame sharded over `ngpus` devices inside the call (same bytes and errors)
+    pub fn compressFrameMultiGpu(src: []const u8, dst: []u8, prefs: ?Preferences, ngpus: c_int) Error!usize {
+        const p = toC(prefs);
+        var out: usize = 0;
+        try check(c.b2lz4f_compress_frame_mgpu(src.ptr, src.len, dst.ptr, dst.len, &p, ngpus, &out));
+        return out;
+    }
+    pub fn decompressFrameMultiGpu(src: []const u8, dst: []u8, ngpus: c_int) Error!usize {
+        var out: usize = 0;
+        try check(c.b2lz4f_decompress_frame_mgpu(src.ptr, src.len, dst.ptr, dst.len, ngpus, &out));
         return out;
     }
     pub fn headerSize(src: []const u8) Error!usize {
