@@ -129,6 +129,19 @@ def test_single_process_multi_gpu_calls(z, oracle, bsid, bc, cc):
     assert z.lz4f.compressFrameMultiGPU(b"", sp, ngpus=ngpus) == z.lz4f.compressFrame(b"", sp)
 
 
+@pytest.mark.gpu
+def test_single_process_multi_gpu_hc(z, oracle):
+    """compressHC level 9 through the multi-GPU call: every device keeps its own chain tables"""
+    from zig_lz4_b200 import datagen
+    n = (6 << 20) + 11
+    data = datagen.generate(n, mode=1, seed=2).tobytes()
+    prefs = z.lz4f.Preferences(blockSizeID=4, blockMode=1, blockChecksumFlag=1, compressionLevel=9)
+    want = oracle.compress_frame(data, oracle.make_prefs(4, 1, 0, 0, 0, 1, 9), threads=8)
+    f = z.lz4f.compressFrameMultiGPU(data, prefs, ngpus=8)
+    assert f == want
+    assert z.lz4f.decompressFrameMultiGPU(f, n, ngpus=8) == data
+
+
 def _one_gpu_result(z, frame, cap):
     try:
         return (0, z.lz4f.decompressFrame(frame, cap))
