@@ -413,6 +413,7 @@ int b2lz4f_decompress_frame(const void* src, size_t n, void* dst, size_t cap, si
 namespace {
 
 std::mutex g_mgpu_mu;
+std::mutex g_mgpu_call_mu;            // one multi-GPU call at a time: its phases leave results in the per-device contexts
 std::vector<b2lz4_ctx*> g_mgpu_ctx;   // one context per device, created on first use, kept for the process
 
 static int mgpu_ctx(int dev, b2lz4_ctx** out) {
@@ -487,6 +488,7 @@ int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap,
     const bool bc = prefs->block_checksum == 1, cc = prefs->content_checksum == 1;
     size_t hsize = 0;
     { int rc = b2lz4f_write_frame_header(dst, cap, prefs, &hsize); if (rc) return rc; }      // :369
+    std::lock_guard<std::mutex> call_lock(g_mgpu_call_mu);
     std::vector<MgpuJob> jobs(G);
     for (int g = 0; g < G; g++) {
         const size_t b0 = (size_t)g * nb / G, b1 = (size_t)(g + 1) * nb / G;
@@ -562,6 +564,7 @@ int b2lz4f_decompress_frame_mgpu(const void* srcv, size_t n, void* dst, size_t c
     const size_t nb = off.size();
     if (!end_mark || nb < (size_t)(4 * G) || (cc && p + 4 > n)) return single();
     if (cap < (nb - 1) * bs + 1) return single();
+    std::unique_lock<std::mutex> call_lock(g_mgpu_call_mu);
     std::vector<MgpuJob> jobs(G);
     for (int g = 0; g < G; g++) {
         const size_t b0 = (size_t)g * nb / G, b1 = (size_t)(g + 1) * nb / G;
@@ -590,7 +593,7 @@ int b2lz4f_decompress_frame_mgpu(const void* srcv, size_t n, void* dst, size_t c
     });
     bool usual = first_error(jobs) == B2LZ4_OK;
     for (int g = 0; usual && g + 1 < G; g++) usual = jobs[g].produced == jobs[g].blocks * bs;
-    if (!usual) return single();   // exact error kind / foreign layout: the serial-order semantics of the one-GPU path
+    if (!usual) { call_lock.unlock(); return single(); }   // exact error kind / foreign layout: the serial-order semantics of the one-GPU path
     if (cc) {                      // src/lz4f.zig:625-635
         uint32_t csum = 0;
         int rc = mgpu_content_sum(jobs, true, &csum); if (rc) return rc;
