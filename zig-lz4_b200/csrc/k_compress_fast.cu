@@ -264,9 +264,20 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
         const uint32_t seq_end = op + LL + 3;
         if (seq_end > cap) return false;                         // monotone in op: see DESIGN.md
         const int32_t t = (int32_t)lane - 1 - (int32_t)LL;           // < 0: token / literal lanes, 0 and 1: offset bytes
-        uint32_t bv = t >= 0 ? offset >> (8 * t) : (lit_in_lanes ? litb : (uint32_t)__ldg(src + anchor + (lane ? lane - 1 : 0)));
-        if (lane == 0) bv = (LL << 4) | ml;
-        if (t < 2) dst[op + lane] = (uint8_t)bv;
+        // Straight-line on purpose (predicated load and store in PTX): as `?:` / `if` this was two divergent regions
+        // with their BSSY/BSYNC pairs, a third of the instructions issued per sequence.
+        uint32_t bv = litb;
+        {
+            const uint32_t need = (!lit_in_lanes && t < 0) ? 1u : 0u;   // literals not in the window's registers (chained window)
+            const uint8_t* lp = src + anchor + (lane ? lane - 1 : 0);
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u8 %0, [%2];\n\t}"
+                : "+r"(bv) : "r"(need), "l"(__cvta_generic_to_global(lp)));
+        }
+        const uint32_t ob = t == 0 ? offset : offset >> 8;
+        bv = t >= 0 ? ob : bv;
+        bv = lane == 0 ? ((LL << 4) | ml) : bv;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %0, 2;\n\t@p st.global.u8 [%1], %2;\n\t}"
+                     :: "r"(t), "l"(__cvta_generic_to_global(dst + op + lane)), "r"(bv) : "memory");
         op = seq_end;
     } else {
         // the caller computes the size itself, so that `op` never depends on a call result
