@@ -443,8 +443,11 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 nfw = nfw < 3 ? nfw : 3;
                 const uint32_t navail = 4 * nfw < nmb ? 4 * nfw : nmb;
                 const uint32_t x1 = F1 ^ m1, x2 = F2 ^ m2, x3 = F3 ^ m3;
-                const uint32_t d = x1 ? (uint32_t)(__ffs(x1) - 1) >> 3
-                                      : 4 + (x2 ? (uint32_t)(__ffs(x2) - 1) >> 3 : 4 + (x3 ? (uint32_t)(__ffs(x3) - 1) >> 3 : 4u));
+                // equal leading bytes of each word, branch-free: clz(brev(0)) = 32 -> 4 (as nested ?: this was two
+                // divergent regions per window)
+                const uint32_t c1 = (uint32_t)__clz(__brev(x1)) >> 3, c2 = (uint32_t)__clz(__brev(x2)) >> 3,
+                               c3 = (uint32_t)__clz(__brev(x3)) >> 3;
+                const uint32_t d = c1 + (c1 == 4 ? c2 + (c2 == 4 ? c3 : 0u) : 0u);
                 const bool more_bytes = d >= navail && p + MINMATCH + navail < mlimit;
                 mlpk = (d < navail ? d : navail) | (more_bytes ? 0x100u : 0u);
             }
