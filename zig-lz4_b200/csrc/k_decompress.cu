@@ -384,17 +384,19 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
-    // occupancy variant: 8 CTAs x 4 warps (<= 64 registers, no spills) or 10 (<= 48 registers); B2_K2_OCC picks
+    // CTAs of 4 warps per SM: 10 (<= 48 registers, no spills) by default — text 5.47 -> 5.31 ms, binary 5.94 -> 5.66 ms per GiB
+    // against 8 (64 registers); 12 and 16 spill and lose (6.2 / 8.4 ms) except on stored blocks.  B2_K2_OCC picks another.
     static int occ = 0;
-    if (!occ) { const char* e = getenv("B2_K2_OCC"); occ = (e && atoi(e) == 10) ? 10 : 8; }
+    if (!occ) { const char* e = getenv("B2_K2_OCC"); int v = e ? atoi(e) : 0; occ = (v == 8 || v == 12 || v == 16) ? v : 10; }
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
-    if (occ == 10)
-        k_decompress<10><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len,
-                                                          dict != nullptr ? 1 : 0, ticket);
-    else
-        k_decompress<8><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len,
-                                                         dict != nullptr ? 1 : 0, ticket);
+#define B2_K2_LAUNCH(N) k_decompress<N><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len, \
+                                                                          dict != nullptr ? 1 : 0, ticket)
+    if (occ == 16) B2_K2_LAUNCH(16);
+    else if (occ == 12) B2_K2_LAUNCH(12);
+    else if (occ == 10) B2_K2_LAUNCH(10);
+    else B2_K2_LAUNCH(8);
+#undef B2_K2_LAUNCH
     count_launch();
     return cudaGetLastError();
 }
