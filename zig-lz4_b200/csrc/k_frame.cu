@@ -74,14 +74,15 @@ cudaError_t launch_scan_records(const uint32_t* csize, const int32_t* status, ui
 // One warp per block record: header word, payload (compressed slot or raw input), optional checksum.
 constexpr int ASM_WARPS = 8;
 
-__global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble(BlockSet slots, BlockSet raw, const uint32_t* __restrict__ csize,
-                                                             const uint32_t* __restrict__ sums,
-                                                             const uint64_t* __restrict__ rec_off, uint8_t* __restrict__ body,
-                                                             uint32_t nblocks, uint32_t block_checksum) {
-    const uint32_t lane = lane_id();
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = warp; i < nblocks; i += nwarps) {
+// One CTA per record (was one warp: 58 registers, a quarter of the warps active, every block the latency of one warp's
+// loop): 256 threads stream the payload with 16-byte accesses, the source realigned in registers.
+__global__ void __launch_bounds__(ASM_WARPS * 32, 8) k_assemble(BlockSet slots, BlockSet raw, const uint32_t* __restrict__ csize,
+                                                                const uint32_t* __restrict__ sums,
+                                                                const uint64_t* __restrict__ rec_off, uint8_t* __restrict__ body,
+                                                                uint32_t nblocks, uint32_t block_checksum) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t NT = ASM_WARPS * 32;
+    for (uint32_t i = blockIdx.x; i < nblocks; i += gridDim.x) {
         const uint8_t* rp; uint32_t rn;
         raw.get(i, rp, rn);
         const uint32_t c = csize[i];
@@ -90,9 +91,28 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble(BlockSet slots, Blo
         if (!store_raw) { const uint8_t* sp; uint32_t sn; slots.get(i, sp, sn); p = sp; n = c; }
         uint8_t* d = body + rec_off[i];
         const uint32_t hw = n | (store_raw ? 0x80000000u : 0u);          // :411-414
-        if (lane < 4) d[lane] = (uint8_t)(hw >> (8 * lane));             // :418
-        warp_copy<true>(d + 4, p, n, lane);
-        if (block_checksum && lane < 4) d[4 + n + lane] = (uint8_t)(sums[i] >> (8 * lane));  // :422-427
+        if (tid < 4) d[tid] = (uint8_t)(hw >> (8 * tid));                // :418
+        if (block_checksum && tid >= 32 && tid < 36) d[4 + n + (tid - 32)] = (uint8_t)(sums[i] >> (8 * (tid - 32)));  // :422-427
+        d += 4;
+        // head bytes up to the first 16-byte boundary of the destination, then vectors, then the tail
+        uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+        if (head > n) head = n;
+        if (tid < head) d[tid] = __ldg(p + tid);
+        const uint8_t* ps = p + head;
+        uint8_t* pd = d + head;
+        const uint32_t rest = n - head, nvec = rest >> 4;
+        const uint32_t bo = (uint32_t)(reinterpret_cast<uintptr_t>(ps) & 15);
+        const uint4* s16 = reinterpret_cast<const uint4*>(ps - bo);
+        uint4* d16 = reinterpret_cast<uint4*>(pd);
+        if (bo == 0) {
+#pragma unroll 4
+            for (uint32_t v = tid; v < nvec; v += NT) d16[v] = __ldg(s16 + v);
+        } else {
+#pragma unroll 4
+            for (uint32_t v = tid; v < nvec; v += NT) d16[v] = extract16(__ldg(s16 + v), __ldg(s16 + v + 1), bo);
+        }
+        const uint32_t done = nvec << 4, tail = rest - done;
+        if (tid < tail) pd[done + tid] = __ldg(ps + done + tid);
     }
 }
 
@@ -100,10 +120,9 @@ cudaError_t launch_assemble(const BlockSet& slots, const BlockSet& raw, const ui
                             const uint64_t* rec_off, uint8_t* body, uint32_t nblocks, uint32_t block_checksum,
                             int num_sms, cudaStream_t stream) {
     if (nblocks == 0) return cudaSuccess;
-    uint32_t want = (nblocks + ASM_WARPS - 1) / ASM_WARPS;
     uint32_t maxg = (uint32_t)num_sms * 8;
-    k_assemble<<<want < maxg ? want : maxg, ASM_WARPS * 32, 0, stream>>>(slots, raw, csize, sums, rec_off, body, nblocks,
-                                                                      block_checksum);
+    k_assemble<<<nblocks < maxg ? nblocks : maxg, ASM_WARPS * 32, 0, stream>>>(slots, raw, csize, sums, rec_off, body, nblocks,
+                                                                            block_checksum);
     count_launch();
     return cudaGetLastError();
 }
