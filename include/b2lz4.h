@@ -80,6 +80,11 @@ B2LZ4_API const char* b2lz4_last_cuda_error(void);
 /* Number of CUDA kernels this library has launched in this process (monotone counter). */
 B2LZ4_API uint64_t b2lz4_kernel_launch_count(void);
 B2LZ4_API const char* b2lz4_version(void);
+/* Diagnostic knob (process-wide; 0 restores the shipped default): "k1_ctas", "k2_occ", "k2_variant", "k3_variant",
+ * "pipe_blocks", "no_pipeline", "serial_walk", "xxh_variant", "spare0".."spare7".  Returns the previous value, -1 for an
+ * unknown key.  Used by the experiments in DESIGN.md and by tests that force a rare path; the library never reads
+ * the environment. */
+B2LZ4_API int b2lz4_debug_tune(const char* key, int value);
 
 /* ------------------------------------------------------------------ context ---- */
 /* One context = one GPU + its workspace (block slots, size/offset tables, pinned staging) and a

@@ -317,27 +317,27 @@ def test_parallel_index_equals_serial_walk(z, oracle, ctx):
     zp, op = both_prefs(z, oracle, dict(block_mode=1, block_checksum=1, content_checksum=1), len(data))
     f = z.lz4f.compressFrame(data, zp)
     assert z.lz4f.decompressFrame(f, len(data)) == data
-    code = ("import sys; sys.path.insert(0, %r); import zig_lz4_b200 as z; f = open(sys.argv[1], 'rb').read(); "
+    code = ("import sys; sys.path.insert(0, %r); import zig_lz4_b200 as z; z.debug_tune('serial_walk', 1); "
+            "f = open(sys.argv[1], 'rb').read(); "
             "d = z.lz4f.decompressFrame(f, int(sys.argv[2])); import hashlib; print(hashlib.sha1(d).hexdigest())")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import hashlib
     import tempfile
     with tempfile.NamedTemporaryFile(suffix=".lz4") as tf:
         tf.write(f); tf.flush()
-        env = dict(os.environ, B2_SERIAL_WALK="1")
-        out = subprocess.run([sys.executable, "-c", code % root, tf.name, str(len(data))], env=env, capture_output=True,
+        out = subprocess.run([sys.executable, "-c", code % root, tf.name, str(len(data))], capture_output=True,
                              text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip() == hashlib.sha1(data).hexdigest()
 
 
 @pytest.fixture
-def small_pipeline_chunks(monkeypatch):
+def small_pipeline_chunks(z):
     """makes the host-pointer frame calls pipeline (upload | kernels | download on three streams) with 24-block
     chunks, so that frames of a few MiB go through the chunked path"""
-    monkeypatch.setenv("B2_PIPE_BLOCKS", "24")
+    z.debug_tune("pipe_blocks", 24)
     yield
-    monkeypatch.delenv("B2_PIPE_BLOCKS", raising=False)
+    z.debug_tune("pipe_blocks", 0)
 
 
 @pytest.mark.parametrize("kw", PREFS + [dict(compression_level=9, block_checksum=1, content_checksum=1)])

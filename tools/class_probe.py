@@ -12,7 +12,11 @@ ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--block-id", type=int, default=4)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--classes", default="text,binary,redundant,random,mixed")
+ap.add_argument("--tune", default="", help="comma-separated b2lz4_debug_tune knobs, e.g. k2_variant=1,k2_occ=8")
 a = ap.parse_args()
+for kv in filter(None, a.tune.split(",")):
+    k, v = kv.split("=")
+    z.debug_tune(k, int(v))
 n = a.mib << 20
 ctx = z.Context(0)
 ctx.set_timing(True)
@@ -34,6 +38,6 @@ for name, mode in (("text", 0), ("binary", 1), ("redundant", 2), ("random", 3), 
         pd = ctx.last_phase_ms()
         best_c = min(best_c, pc[0]); best_d = min(best_d, pd[0]); best_i = min(best_i, pd[2])
     assert m == n and torch.equal(back[:n], src)
-    print(json.dumps({"class": name, "mib": a.mib, "ratio": round(n / cs, 3), "k1_ms": round(best_c, 3),
+    print(json.dumps({"tune": a.tune, "class": name, "mib": a.mib, "ratio": round(n / cs, 3), "k1_ms": round(best_c, 3),
                       "k1_gbs": round(n / best_c / 1e6, 1), "k2_ms": round(best_d, 3), "k2_gbs": round(n / best_d / 1e6, 1),
                       "index_ms": round(best_i, 3)}), flush=True)

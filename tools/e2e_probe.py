@@ -16,9 +16,8 @@ hback = torch.empty(n, dtype=torch.uint8).pin_memory()
 import ctypes as C
 def arr(t, k): return np.frombuffer((C.c_uint8 * k).from_address(t.data_ptr()), dtype=np.uint8)
 hs, hd, hb = arr(host, n), arr(hcomp, cap), arr(hback, n)
-for label, env in (("pipelined", {}), ("blocks1024", {"B2_PIPE_BLOCKS": "1024"}), ("blocks512", {"B2_PIPE_BLOCKS": "512"}), ("blocks4096", {"B2_PIPE_BLOCKS": "4096"}), ("oneshot", {"B2_NO_PIPELINE": "1"})):
-    for k in ("B2_PIPE_BLOCKS", "B2_NO_PIPELINE"): os.environ.pop(k, None)
-    os.environ.update(env)
+for label, knobs in (("pipelined", {}), ("blocks1024", {"pipe_blocks": 1024}), ("blocks512", {"pipe_blocks": 512}), ("blocks4096", {"pipe_blocks": 4096}), ("oneshot", {"no_pipeline": 1})):
+    for k in ("pipe_blocks", "no_pipeline"): z.debug_tune(k, knobs.get(k, 0))
     for it in range(3):
         t0 = time.perf_counter(); cs = ctx.compress_frame(hs, zp, dst=hd); t1 = time.perf_counter()
         m = ctx.decompress_frame(hd[:cs], dst=hb); t2 = time.perf_counter()

@@ -10,7 +10,7 @@ Import name: the directory is called ``zig-lz4_b200`` (not a valid identifier); 
 the repo root aliases it, so ``import zig_lz4_b200`` works.
 """
 from . import _native
-from ._native import (B2Error, lib, build, library_path, kernel_launch_count, Context, Prefs, status_name)
+from ._native import (B2Error, lib, build, library_path, kernel_launch_count, debug_tune, Context, Prefs, status_name)
 from . import lz4, lz4hc, lz4f
 
 # ---- flat re-exports, reference src/root.zig:7-57 ----
@@ -29,4 +29,4 @@ LZ4HC_CLEVEL_DEFAULT = lz4hc.LZ4HC_CLEVEL_DEFAULT
 LZ4HC_CLEVEL_MAX = lz4hc.LZ4HC_CLEVEL_MAX
 
 __all__ = ["lz4", "lz4hc", "lz4f", "B2Error", "Context", "Prefs", "lib", "build", "library_path",
-           "kernel_launch_count", "status_name"]
+           "kernel_launch_count", "debug_tune", "status_name"]

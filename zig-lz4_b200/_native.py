@@ -84,7 +84,7 @@ def build(force=False, verbose=False):
 _lib = None
 
 EXPORTS = [
-    "b2lz4_status_name", "b2lz4_last_cuda_error", "b2lz4_kernel_launch_count", "b2lz4_version",
+    "b2lz4_status_name", "b2lz4_last_cuda_error", "b2lz4_kernel_launch_count", "b2lz4_version", "b2lz4_debug_tune",
     "b2lz4_ctx_create", "b2lz4_ctx_destroy", "b2lz4_ctx_device", "b2lz4_ctx_workspace_bytes",
     "b2lz4_compress_bound", "b2lz4_compress_default", "b2lz4_compress_fast", "b2lz4_decompress_safe",
     "b2lz4_decompress_safe_using_dict", "b2lz4_compress_hc", "b2lz4_xxh32",
@@ -120,6 +120,7 @@ def lib():
     L.b2lz4_last_cuda_error.restype = C.c_char_p
     L.b2lz4_kernel_launch_count.restype = C.c_uint64
     L.b2lz4_version.restype = C.c_char_p
+    L.b2lz4_debug_tune.argtypes = [C.c_char_p, i32]
     L.b2lz4_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.b2lz4_ctx_destroy.argtypes = [vp]
     L.b2lz4_ctx_destroy.restype = None
@@ -194,6 +195,14 @@ def check(rc):
 
 def kernel_launch_count():
     return lib().b2lz4_kernel_launch_count()
+
+
+def debug_tune(key, value):
+    """Diagnostic knob of the library (include/b2lz4.h b2lz4_debug_tune); returns the previous value."""
+    old = lib().b2lz4_debug_tune(key.encode(), int(value))
+    if old < 0:
+        raise KeyError(key)
+    return old
 
 
 def as_buffer(b):

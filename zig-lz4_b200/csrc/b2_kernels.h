@@ -8,6 +8,22 @@ namespace b2 {
 
 void count_launch();  // bumps the process-wide kernel launch counter (b2lz4_kernel_launch_count)
 
+// Diagnostic knobs (b2lz4_debug_tune, include/b2lz4.h): process-wide, 0 = the shipped default.  They exist for the
+// occupancy / variant experiments recorded in DESIGN.md and for tests that force a rare path; nothing reads the
+// environment on a launch path.
+struct Tune {
+    int k1_ctas;        // K1: CTAs per SM (u16-table kernel), 1..9
+    int k2_occ;         // K2: CTAs of 4 warps per SM: 8, 10, 12
+    int k2_variant;     // K2: 1 = round-1 decoder (serial token walk), else the chunked decoder
+    int k3_variant;     // K3 experiments
+    int pipe_blocks;    // host-pointer frame pipeline: blocks per chunk (tests pipeline small frames with it)
+    int no_pipeline;    // host-pointer frame calls take the one-shot path
+    int serial_walk;    // frame index: force the serial header walk (K7) instead of the parallel index (K7')
+    int xxh_variant;    // content checksum experiments
+    int spare[8];
+};
+Tune& tune();
+
 // K1 — fast compressor (k_compress_fast.cu)
 cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
                                  uint32_t nblocks, uint32_t max_len, uint32_t accel, uint32_t* ticket, int num_sms,

@@ -15,6 +15,9 @@ namespace b2 {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static Tune g_tune = {};
+Tune& tune() { return g_tune; }
+
 static thread_local std::string g_cuda_err;
 void set_cuda_error(cudaError_t e, const char* what) {
     g_cuda_err = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " @ " + what;
@@ -97,7 +100,20 @@ const char* b2lz4_status_name(int s) {
 }
 const char* b2lz4_last_cuda_error(void) { return g_cuda_err.c_str(); }
 uint64_t b2lz4_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-const char* b2lz4_version(void) { return "b2lz4 0.1 (sm_100a)"; }
+const char* b2lz4_version(void) { return "b2lz4 0.2 (sm_100a)"; }
+int b2lz4_debug_tune(const char* key, int value) {
+    if (!key) return -1;
+    b2::Tune& t = b2::tune();
+    const std::string k(key);
+    int* slot = k == "k1_ctas" ? &t.k1_ctas : k == "k2_occ" ? &t.k2_occ : k == "k2_variant" ? &t.k2_variant
+              : k == "k3_variant" ? &t.k3_variant : k == "pipe_blocks" ? &t.pipe_blocks : k == "no_pipeline" ? &t.no_pipeline
+              : k == "serial_walk" ? &t.serial_walk : k == "xxh_variant" ? &t.xxh_variant : nullptr;
+    if (!slot && k.rfind("spare", 0) == 0 && k.size() == 6 && k[5] >= '0' && k[5] <= '7') slot = &t.spare[k[5] - '0'];
+    if (!slot) return -1;
+    const int old = *slot;
+    *slot = value;
+    return old;
+}
 
 // ================================================================ context
 int b2lz4_ctx_create(int device, b2lz4_ctx** out) {
@@ -519,7 +535,7 @@ static int decode_blocks_dev(b2lz4_ctx* c, const uint8_t* src, uint64_t n, const
 // the candidate list is implausibly long or a header above `bound` sits on the chain.
 static int build_block_index(b2lz4_ctx* c, const uint8_t* src, uint64_t n, uint64_t start, uint32_t bound, bool bc,
                              cudaStream_t s, WalkResult* wout) {
-    static const bool force_serial = getenv("B2_SERIAL_WALK") != nullptr;
+    const bool force_serial = tune().serial_walk != 0;
     if (!force_serial && n > start) {
         const uint32_t ntiles = index_tiles(src, n);
         uint64_t cap_nodes = (n - start) / 64 + 4096;

@@ -94,18 +94,18 @@ static int decompress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void
 // A chunk must hold enough blocks to fill the GPU (one warp per block, ~4000 warps resident), so chunks
 // are sized in blocks: 2048 blocks (three chunks in flight keep the GPU full), at most 256 MiB of raw data; frames whose block size leaves fewer
 // than 1024 blocks per chunk (1 MiB / 4 MiB blocks) and frames shorter than three chunks take the
-// one-shot path.  B2_PIPE_BLOCKS overrides the block count (tests use it to pipeline small frames).
+// one-shot path.  b2lz4_debug_tune("pipe_blocks") overrides the block count (tests use it to pipeline small frames).
 constexpr size_t PIPE_MAX_CHUNK = 256u << 20;
 static size_t pipe_blocks_for(size_t bs, bool* forced) {
-    const char* e = getenv("B2_PIPE_BLOCKS");
-    if (e && atol(e) > 0) { *forced = true; return (size_t)atol(e); }
+    const int forced_blocks = b2::tune().pipe_blocks;
+    if (forced_blocks > 0) { *forced = true; return (size_t)forced_blocks; }
     *forced = false;
     size_t blocks = 2048;
     if (blocks * bs > PIPE_MAX_CHUNK) blocks = PIPE_MAX_CHUNK / bs;
     return blocks;
 }
 static bool pipeline_applies(size_t raw_bytes, size_t bs, size_t* chunk_blocks) {
-    if (getenv("B2_NO_PIPELINE")) return false;
+    if (b2::tune().no_pipeline) return false;
     bool forced;
     const size_t blocks = pipe_blocks_for(bs, &forced);
     *chunk_blocks = blocks;

@@ -6,10 +6,17 @@
 // (src.len == 0 -> 0, dst.len == 0 -> 0 without error, :97-98).
 //
 // Two tiers share one block:
-//   FAST tier (decode_block_fast): the token chain is the only serial part of LZ4 decoding, so the warp
-//   walks it for up to 32 sequences at a time touching nothing but the token bytes (one uniform byte
-//   load + ~8 integer ops per sequence), hands sequence k to lane k, and then all 32 sequences are
-//   expanded at once: a warp scan of (LL + ML) gives every lane its output position, each lane copies
+//   FAST tier (decode_block_fast): the token chain is the only serial part of LZ4 decoding.  Where a token
+//   starts depends on the whole chain before it, but how long a token is does not: it is a function of the
+//   bytes at its position alone.  So the warp first loads the next 256 bytes of the stream coalesced into
+//   shared memory and computes, for EVERY byte position at once (8 positions per lane, four per 32-bit SIMD
+//   word), the distance to the next token *if* a token started there: 3 + LL for a plain token, the same plus
+//   the length-extension bytes for one LL byte and up to two ML bytes, 0 ("halt") for anything longer, too
+//   close to the end of the stream, or running off it.  The serial part is then a chain of 32 dependent
+//   shared-memory reads `p += delta[p]` (3 instructions per sequence instead of ~19: the round-1 walk issued a
+//   global byte load and decoded the token on all 32 lanes for every sequence — half of the kernel's
+//   instructions).  Sequence k goes to lane k, which decodes its own token from the staged bytes, and then
+//   all 32 sequences are expanded at once: a warp scan of (LL + ML) gives every lane its output position, each lane copies
 //   its own literal run, and the match copies are resolved in dependency rounds (a lane may copy once
 //   no pending match of an earlier lane overlaps its source range; the first pending lane always may,
 //   so the rounds terminate; a lane's own forward overlap, offset < length, is safe because one thread
@@ -29,7 +36,6 @@
 //     continue at dst[0..].
 #include "b2_common.cuh"
 #include "b2_kernels.h"
-#include <cstdlib>
 
 namespace b2 {
 
@@ -75,6 +81,67 @@ __device__ __forceinline__ void match_copy(uint8_t* d, const uint8_t* s, uint32_
     }
 }
 
+// One sequence of the reference's loop (src/lz4.zig:111-248) at (ip, op), checks in the reference's order.
+// Returns 0 = go on, 1 = the stream ended normally (:113 / :146), 2 = error (st set).
+template <bool WRITE>
+__device__ __forceinline__ int exact_step(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                          const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                          uint32_t& ip, uint32_t& op, int& st) {
+    const uint32_t iend = n, oend = cap;
+    if (ip >= iend) return 1;                                       // :113
+    const uint32_t token = __ldg(src + ip);
+    ip += 1;
+    uint32_t LL = token >> 4;
+    if (LL == RUN_MASK) {                                           // :123
+        if (!read_len_ext(src, ip, iend, LL, lane)) { st = ST_CORRUPTED; return 2; }
+    }
+    if (LL > 0) {                                                   // :134
+        if ((uint64_t)ip + LL > iend) { st = ST_CORRUPTED; return 2; }
+        if ((uint64_t)op + LL > oend) { st = ST_OUTPUT_TOO_SMALL; return 2; }
+        if (WRITE) warp_copy<true>(dst + op, src + ip, LL, lane);
+        ip += LL;
+        op += LL;
+    }
+    if (ip >= iend) return 1;                                       // :146
+    if (ip + 2 > iend) { st = ST_CORRUPTED; return 2; }             // :149
+    const uint32_t offset = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
+    ip += 2;
+    if (offset == 0) { st = ST_CORRUPTED; return 2; }               // :154
+    uint32_t ML = token & ML_MASK;
+    if (ML == ML_MASK) {                                            // :160
+        if (!read_len_ext(src, ip, iend, ML, lane)) { st = ST_CORRUPTED; return 2; }
+    }
+    ML += MINMATCH;                                                 // :171
+    if ((uint64_t)op + ML > oend) { st = ST_OUTPUT_TOO_SMALL; return 2; }  // :174
+    if (offset > op) {                                              // :181 match starts before dst
+        if (!has_dict) { st = ST_CORRUPTED; return 2; }             // :183-186
+        if ((uint64_t)offset > (uint64_t)op + dict_len) { st = ST_CORRUPTED; return 2; }  // :190
+        const uint32_t back = offset - op;                          // lowPrefixOffset, :195
+        const uint8_t* dm = dict + dict_len - back;                 // :196
+        if (WRITE) {
+            __syncwarp();
+            if (ML <= back) {                                       // :199
+                warp_copy<true>(dst + op, dm, ML, lane);
+            } else {
+                warp_copy<true>(dst + op, dm, back, lane);
+                __syncwarp();
+                // rest continues at dst[0..] (:213-227): forward copy, may overlap itself
+                match_copy(dst + op + back, dst, op + back, ML - back, lane);
+            }
+            __syncwarp();
+        }
+        op += ML;
+    } else {
+        if (WRITE) {
+            __syncwarp();  // literals written by other lanes must be visible
+            match_copy(dst + op, dst + op - offset, offset, ML, lane);  // :232-246
+            __syncwarp();
+        }
+        op += ML;
+    }
+    return 0;
+}
+
 template <bool WRITE>
 __device__ void decode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
                              const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
@@ -83,59 +150,10 @@ __device__ void decode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_
     olen = 0;
     if (n == 0) return;    // :97
     if (cap == 0) return;  // :98
-    const uint32_t iend = n, oend = cap;
     for (;;) {
-        if (ip >= iend) break;                                          // :113
-        const uint32_t token = __ldg(src + ip);
-        ip += 1;
-        uint32_t LL = token >> 4;
-        if (LL == RUN_MASK) {                                           // :123
-            if (!read_len_ext(src, ip, iend, LL, lane)) { st = ST_CORRUPTED; return; }
-        }
-        if (LL > 0) {                                                   // :134
-            if ((uint64_t)ip + LL > iend) { st = ST_CORRUPTED; return; }
-            if ((uint64_t)op + LL > oend) { st = ST_OUTPUT_TOO_SMALL; return; }
-            if (WRITE) warp_copy<true>(dst + op, src + ip, LL, lane);
-            ip += LL;
-            op += LL;
-        }
-        if (ip >= iend) break;                                          // :146
-        if (ip + 2 > iend) { st = ST_CORRUPTED; return; }               // :149
-        const uint32_t offset = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
-        ip += 2;
-        if (offset == 0) { st = ST_CORRUPTED; return; }                 // :154
-        uint32_t ML = token & ML_MASK;
-        if (ML == ML_MASK) {                                            // :160
-            if (!read_len_ext(src, ip, iend, ML, lane)) { st = ST_CORRUPTED; return; }
-        }
-        ML += MINMATCH;                                                 // :171
-        if ((uint64_t)op + ML > oend) { st = ST_OUTPUT_TOO_SMALL; return; }  // :174
-        if (offset > op) {                                              // :181 match starts before dst
-            if (!has_dict) { st = ST_CORRUPTED; return; }               // :183-186
-            if ((uint64_t)offset > (uint64_t)op + dict_len) { st = ST_CORRUPTED; return; }  // :190
-            const uint32_t back = offset - op;                          // lowPrefixOffset, :195
-            const uint8_t* dm = dict + dict_len - back;                 // :196
-            if (WRITE) {
-                __syncwarp();
-                if (ML <= back) {                                       // :199
-                    warp_copy<true>(dst + op, dm, ML, lane);
-                } else {
-                    warp_copy<true>(dst + op, dm, back, lane);
-                    __syncwarp();
-                    // rest continues at dst[0..] (:213-227): forward copy, may overlap itself
-                    match_copy(dst + op + back, dst, op + back, ML - back, lane);
-                }
-                __syncwarp();
-            }
-            op += ML;
-        } else {
-            if (WRITE) {
-                __syncwarp();  // literals written by other lanes must be visible
-                match_copy(dst + op, dst + op - offset, offset, ML, lane);  // :232-246
-                __syncwarp();
-            }
-            op += ML;
-        }
+        const int r = exact_step<WRITE>(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, st);
+        if (r == 2) return;
+        if (r == 1) break;
     }
     olen = op;
 }
@@ -171,15 +189,132 @@ __device__ __forceinline__ uint32_t count_le(uint32_t sorted_v, uint32_t x) {
     return c;
 }
 
-__device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
-                                  const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
-                                  uint32_t& olen, int& st) {
+// Expands one batch: lanes < k hold a sequence each (literals at src + myLit, myLL of them, then a 2-byte offset; match
+// length myML), in stream order; output continues at op.  Returns false — nothing this batch wrote matters — when a
+// sequence needs the exact tier's judgement: offset 0 (:154), a match reaching before dst (:181 / :231), output
+// overflow (:137 / :174).
+__device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, uint8_t* dst, uint32_t cap, uint32_t lane,
+                                             uint32_t k, uint32_t myLit, uint32_t myLL, uint32_t myML, uint32_t& op) {
+    const bool valid = lane < k;
+    uint32_t off = 1;
+    if (valid) off = (uint32_t)__ldg(src + myLit + myLL) | ((uint32_t)__ldg(src + myLit + myLL + 1) << 8);
+    const uint32_t len = myLL + myML;  // 0 on idle lanes
+    const uint32_t incl = warp_incl_scan(len, lane);
+    const uint32_t o0 = op + incl - len;         // where this sequence's literals go
+    const uint32_t ms = o0 + myLL;               // where its match goes
+    const uint32_t batch_len = __shfl_sync(FULL, incl, 31);
+    const bool odd = valid && (off == 0 || off > ms);
+    if (__ballot_sync(FULL, odd) != 0 || batch_len > cap - op) return false;
+
+    // literals: every lane copies its own short run, long runs go warp-wide
+    {
+        const bool lng = myLL > LONG_SEQ;
+        const uint32_t nl = lng ? 0u : myLL;
+        const uint32_t mx = __reduce_max_sync(FULL, nl);
+        const uint8_t* ls = src + myLit;
+        uint8_t* ld = dst + o0;
+        uint32_t rem = nl;
+        for (uint32_t i0 = 0; i0 < mx; i0 += 4) {
+            uint32_t r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if ((uint32_t)u < rem) r[u] = __ldg(ls + u);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if ((uint32_t)u < rem) ld[u] = (uint8_t)r[u];
+            ls += 4; ld += 4;
+            rem = rem > 4 ? rem - 4 : 0u;
+        }
+        uint32_t lm = __ballot_sync(FULL, lng);
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            warp_copy<true>(dst + __shfl_sync(FULL, o0, j), src + __shfl_sync(FULL, myLit, j),
+                            __shfl_sync(FULL, myLL, j), lane);
+        }
+    }
+    __syncwarp();
+
+    // matches: dependency rounds
+    {
+        const uint32_t s = ms - off;                           // source start
+        const uint32_t e = (off < myML) ? ms : s + myML;       // source end outside its own output
+        const uint32_t mend = valid ? ms + myML : 0xFFFFFFFFu; // non-decreasing across lanes
+        const uint32_t mstart = valid ? ms : 0xFFFFFFFFu;
+        uint32_t dep = 0;
+        if (__ballot_sync(FULL, valid && e > op) != 0) {
+            // lanes [lo, hi) hold the matches that overlap [s, e): mend_j > s and ms_j < e
+            const uint32_t lo = count_le(mend, s);
+            const uint32_t hi = count_le(mstart, e - 1);
+            dep = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+        }
+        const bool lng = myML > LONG_SEQ;
+        // a short self-overlapping match with offset < 8 repeats a pattern that fits one register pair
+        const bool tiny = !lng && off < 8 && off < myML;
+        bool pending = valid;
+        uint32_t pm = __ballot_sync(FULL, pending);
+        while (pm) {
+            const bool go = pending && (pm & dep) == 0;
+            uint8_t* md = dst + ms;
+            const uint8_t* msrc = dst + s;
+            {   // 8 bytes at a time: all loads of a chunk are issued before its stores.  Safe for a
+                // self-overlapping match with offset >= 8: a chunk only reads bytes of earlier chunks.
+                const uint32_t nm = (go && !lng && !tiny) ? myML : 0u;
+                const uint32_t mx = __reduce_max_sync(FULL, nm);
+                // one pair of running pointers and one remaining-byte count per lane: the accesses are
+                // base + immediate under a predicate (not a re-derived 64-bit address per byte)
+                const uint8_t* ps = msrc;
+                uint8_t* pd = md;
+                uint32_t rem = nm;
+                for (uint32_t i0 = 0; i0 < mx; i0 += 8) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if ((uint32_t)u < rem) r[u] = ps[u];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if ((uint32_t)u < rem) pd[u] = (uint8_t)r[u];
+                    ps += 8; pd += 8;
+                    rem = rem > 8 ? rem - 8 : 0u;
+                }
+            }
+            if (__ballot_sync(FULL, go && tiny)) {
+                if (go && tiny) {
+                    uint64_t pat = 0;
+                    for (uint32_t i = 0; i < off; i++) pat |= (uint64_t)msrc[i] << (8 * i);
+                    uint32_t j = 0;
+                    for (uint32_t i = 0; i < myML; i++) {
+                        md[i] = (uint8_t)(pat >> (8 * j));
+                        j = (j + 1 == off) ? 0u : j + 1;
+                    }
+                }
+                __syncwarp();
+            }
+            uint32_t gm = __ballot_sync(FULL, go && lng);
+            while (gm) {
+                const int j = __ffs(gm) - 1;
+                gm &= gm - 1;
+                const uint32_t jms = __shfl_sync(FULL, ms, j), joff = __shfl_sync(FULL, off, j);
+                match_copy(dst + jms, dst + jms - joff, joff, __shfl_sync(FULL, myML, j), lane);
+            }
+            if (go) pending = false;
+            __syncwarp();
+            pm = __ballot_sync(FULL, pending);
+        }
+    }
+    op += batch_len;
+    return true;
+}
+
+// Round-1 front end (kept for A/B runs, b2lz4_debug_tune("k2_variant", 1)): the warp walks the token chain itself.
+__device__ void decode_block_fast_v1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                     const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                     uint32_t& olen, int& st) {
     uint32_t ip = 0, op = 0;
     if (n > PLAIN_SPAN && cap > 0) {
         const uint32_t iend = n;
         const uint32_t isafe = n - PLAIN_SPAN;  // plain tokens below this read in bounds without checks
         for (;;) {
-            // ---------------- serial part: walk up to 32 tokens, sequence k goes to lane k ----------------
             const uint32_t ip0 = ip;
             uint32_t myLit = 0, myLL = 0, myML = 0;
             uint32_t k = 0;
@@ -207,116 +342,7 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                 }
             }
             if (k == 0) break;
-            // ---------------- parallel part ----------------
-            const bool valid = lane < k;
-            uint32_t off = 1;
-            if (valid) off = (uint32_t)__ldg(src + myLit + myLL) | ((uint32_t)__ldg(src + myLit + myLL + 1) << 8);
-            const uint32_t len = myLL + myML;  // 0 on idle lanes
-            const uint32_t incl = warp_incl_scan(len, lane);
-            const uint32_t o0 = op + incl - len;         // where this sequence's literals go
-            const uint32_t ms = o0 + myLL;               // where its match goes
-            const uint32_t batch_len = __shfl_sync(FULL, incl, 31);
-            // offset 0 (:154), match before dst (:181/:231), output overflow (:137/:174): exact tier decides
-            const bool odd = valid && (off == 0 || off > ms);
-            if (__ballot_sync(FULL, odd) != 0 || batch_len > cap - op) { ip = ip0; break; }
-
-            // literals: every lane copies its own short run, long runs go warp-wide
-            {
-                const bool lng = myLL > LONG_SEQ;
-                const uint32_t nl = lng ? 0u : myLL;
-                const uint32_t mx = __reduce_max_sync(FULL, nl);
-                const uint8_t* ls = src + myLit;
-                uint8_t* ld = dst + o0;
-                uint32_t rem = nl;
-                for (uint32_t i0 = 0; i0 < mx; i0 += 4) {
-                    uint32_t r[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if ((uint32_t)u < rem) r[u] = __ldg(ls + u);
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if ((uint32_t)u < rem) ld[u] = (uint8_t)r[u];
-                    ls += 4; ld += 4;
-                    rem = rem > 4 ? rem - 4 : 0u;
-                }
-                uint32_t lm = __ballot_sync(FULL, lng);
-                while (lm) {
-                    const int j = __ffs(lm) - 1;
-                    lm &= lm - 1;
-                    warp_copy<true>(dst + __shfl_sync(FULL, o0, j), src + __shfl_sync(FULL, myLit, j),
-                                    __shfl_sync(FULL, myLL, j), lane);
-                }
-            }
-            __syncwarp();
-
-            // matches: dependency rounds
-            {
-                const uint32_t s = ms - off;                           // source start
-                const uint32_t e = (off < myML) ? ms : s + myML;       // source end outside its own output
-                const uint32_t mend = valid ? ms + myML : 0xFFFFFFFFu; // non-decreasing across lanes
-                const uint32_t mstart = valid ? ms : 0xFFFFFFFFu;
-                uint32_t dep = 0;
-                if (__ballot_sync(FULL, valid && e > op) != 0) {
-                    // lanes [lo, hi) hold the matches that overlap [s, e): mend_j > s and ms_j < e
-                    const uint32_t lo = count_le(mend, s);
-                    const uint32_t hi = count_le(mstart, e - 1);
-                    dep = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
-                }
-                const bool lng = myML > LONG_SEQ;
-                // a short self-overlapping match with offset < 8 repeats a pattern that fits one register pair
-                const bool tiny = !lng && off < 8 && off < myML;
-                bool pending = valid;
-                uint32_t pm = __ballot_sync(FULL, pending);
-                while (pm) {
-                    const bool go = pending && (pm & dep) == 0;
-                    uint8_t* md = dst + ms;
-                    const uint8_t* msrc = dst + s;
-                    {   // 8 bytes at a time: all loads of a chunk are issued before its stores.  Safe for a
-                        // self-overlapping match with offset >= 8: a chunk only reads bytes of earlier chunks.
-                        const uint32_t nm = (go && !lng && !tiny) ? myML : 0u;
-                        const uint32_t mx = __reduce_max_sync(FULL, nm);
-                        // one pair of running pointers and one remaining-byte count per lane: the accesses are
-                        // base + immediate under a predicate (not a re-derived 64-bit address per byte)
-                        const uint8_t* ps = msrc;
-                        uint8_t* pd = md;
-                        uint32_t rem = nm;
-                        for (uint32_t i0 = 0; i0 < mx; i0 += 8) {
-                            uint32_t r[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if ((uint32_t)u < rem) r[u] = ps[u];
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if ((uint32_t)u < rem) pd[u] = (uint8_t)r[u];
-                            ps += 8; pd += 8;
-                            rem = rem > 8 ? rem - 8 : 0u;
-                        }
-                    }
-                    if (__ballot_sync(FULL, go && tiny)) {
-                        if (go && tiny) {
-                            uint64_t pat = 0;
-                            for (uint32_t i = 0; i < off; i++) pat |= (uint64_t)msrc[i] << (8 * i);
-                            uint32_t j = 0;
-                            for (uint32_t i = 0; i < myML; i++) {
-                                md[i] = (uint8_t)(pat >> (8 * j));
-                                j = (j + 1 == off) ? 0u : j + 1;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    uint32_t gm = __ballot_sync(FULL, go && lng);
-                    while (gm) {
-                        const int j = __ffs(gm) - 1;
-                        gm &= gm - 1;
-                        const uint32_t jms = __shfl_sync(FULL, ms, j), joff = __shfl_sync(FULL, off, j);
-                        match_copy(dst + jms, dst + jms - joff, joff, __shfl_sync(FULL, myML, j), lane);
-                    }
-                    if (go) pending = false;
-                    __syncwarp();
-                    pm = __ballot_sync(FULL, pending);
-                }
-            }
-            op += batch_len;
+            if (!expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) { ip = ip0; break; }
             if (stop) break;
         }
     }
@@ -324,12 +350,165 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
     decode_block<true>(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, olen, st);
 }
 
-template <int MIN_CTAS>
+// Out-of-line copies of the exact tier for the fast tier's rare exits (values in, values out: a reference parameter
+// would pin the caller's ip / op in local memory for the whole hot loop).
+__device__ __noinline__ uint4 exact_step_ool(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                             const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                             uint32_t ip, uint32_t op) {
+    int st = ST_OK;
+    const int r = exact_step<true>(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, st);
+    return make_uint4(ip, op, (uint32_t)st, (uint32_t)r);
+}
+__device__ __noinline__ uint2 finish_exact_ool(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                               const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                               uint32_t ip, uint32_t op) {
+    uint32_t olen = 0;
+    int st = ST_OK;
+    decode_block<true>(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, olen, st);
+    return make_uint2(olen, (uint32_t)st);
+}
+
+// ---- chunked front end ----
+constexpr uint32_t CHUNK = 256;        // stream bytes whose token lengths are computed at once (8 per lane)
+constexpr uint32_t CHUNK_MARGIN = 32;  // staged bytes after the chunk: length-extension bytes of its last tokens
+constexpr uint32_t DELTA_SLOTS = 544;  // the walk may stand on any position < CHUNK + 2 + 269 + 2 + 2; slots >= CHUNK stay 0
+struct __align__(16) WarpStage {
+    uint8_t bytes[CHUNK + CHUNK_MARGIN];
+    uint16_t delta[DELTA_SLOTS];
+    uint16_t pos[32];
+};
+
+// Token lengths of four positions at once: bytes of `x` are candidate tokens.  d = 2 * (3 + LL) per byte (plain tokens;
+// deltas are kept doubled = as byte offsets into the u16 delta table, one add less per step of the walk);
+// e has bit 4 of a byte set when that token has a length-extension (either nibble 15), and d is cleared there.
+__device__ __forceinline__ void plain_deltas(uint32_t x, uint32_t& d, uint32_t& e) {
+    const uint32_t hi = (x >> 4) & 0x0F0F0F0Fu, lo = x & 0x0F0F0F0Fu;
+    e = ((hi + 0x01010101u) | (lo + 0x01010101u)) & 0x10101010u;
+    d = ((hi << 1) + 0x06060606u) & ~((e >> 4) * 0xFFu);
+}
+
+__device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                  const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                  WarpStage* __restrict__ ws, uint32_t& olen, int& st) {
+    uint32_t ip = 0, op = 0;
+    st = ST_OK;
+    olen = 0;
+    if (n == 0 || cap == 0) return;          // :97-98
+    if (n > PLAIN_SPAN && n < 0x7F000000u) {   // (chunk positions are kept in int32)
+        const uint32_t isafe = n - PLAIN_SPAN;   // a plain token below this reads its offset in bounds and is followed by more stream
+        while (ip < isafe) {
+            // ---------------- stage the next 256 (+32) stream bytes, 8-byte aligned ----------------
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src + ip) & 7);
+            const int32_t cb = (int32_t)ip - (int32_t)sh;          // block position of chunk byte 0 (>= -7)
+            {
+                const uint2* g = reinterpret_cast<const uint2*>(src + cb);
+                uint2 w = make_uint2(0u, 0u);
+                if (cb + 8 * (int32_t)lane < (int32_t)n) w = __ldg(g + lane);   // a word that holds a stream byte is mapped
+                reinterpret_cast<uint2*>(ws->bytes)[lane] = w;
+                if (lane < CHUNK_MARGIN / 8) {
+                    uint2 m = make_uint2(0u, 0u);
+                    if (cb + (int32_t)CHUNK + 8 * (int32_t)lane < (int32_t)n) m = __ldg(g + 32 + lane);
+                    reinterpret_cast<uint2*>(ws->bytes)[32 + lane] = m;
+                }
+                if (lane < 4 && ip + 1024 + lane * 128 < n) prefetch_l2(src + ip + 1024 + lane * 128);
+                // ---------------- distance to the next token from every position ----------------
+                uint32_t d0, d1, e0, e1;
+                plain_deltas(w.x, d0, e0);
+                plain_deltas(w.y, d1, e1);
+                const int32_t lim = (int32_t)isafe - cb;            // positions >= lim are left to the exact tier
+                if (lim < (int32_t)CHUNK) {
+                    const int32_t kv = lim - 8 * (int32_t)lane;      // valid positions of this lane
+                    const uint64_t keep = kv <= 0 ? 0ull : (kv >= 8 ? ~0ull : ((1ull << (8 * kv)) - 1ull));
+                    d0 &= (uint32_t)keep; d1 &= (uint32_t)(keep >> 32);
+                    e0 &= (uint32_t)keep; e1 &= (uint32_t)(keep >> 32);
+                }
+                uint4 dd;
+                dd.x = __byte_perm(d0, 0u, 0x4140); dd.y = __byte_perm(d0, 0u, 0x4342);
+                dd.z = __byte_perm(d1, 0u, 0x4140); dd.w = __byte_perm(d1, 0u, 0x4342);
+                reinterpret_cast<uint4*>(ws->delta)[lane] = dd;
+                __syncwarp();
+                // tokens with length-extension bytes: one LL byte and up to two ML bytes are resolved here
+                uint32_t em = (e0 >> 4) | (e1 >> 3);                 // bit 8j: position j, bit 8j+1: position 4+j
+                while (em) {
+                    const uint32_t b = (uint32_t)__ffs(em) - 1;
+                    em &= em - 1;
+                    const uint32_t p = 8 * lane + 4 * (b & 1) + (b >> 3);
+                    const uint32_t t = ws->bytes[p];
+                    uint32_t LL = t >> 4, q = p + 1;
+                    bool ok = true;
+                    if (LL == RUN_MASK) { const uint32_t x = ws->bytes[q]; ok = x != 255u; LL += x; q += 1; }
+                    q += LL + 2;                                     // past literals and offset
+                    if ((t & ML_MASK) == ML_MASK) {
+                        const uint32_t y = ws->bytes[q < CHUNK + CHUNK_MARGIN - 2 ? q : CHUNK + CHUNK_MARGIN - 2];
+                        const uint32_t y2 = ws->bytes[q < CHUNK + CHUNK_MARGIN - 2 ? q + 1 : CHUNK + CHUNK_MARGIN - 1];
+                        ok = ok && q < CHUNK + CHUNK_MARGIN - 2 && !(y == 255u && y2 == 255u);
+                        q += y == 255u ? 2 : 1;
+                    }
+                    // every byte of the token lies in the stream, and (q <= n - 2 is not needed: :146 only asks ip < iend
+                    // after the literals, which q - 2 - (ML bytes) < n gives) the next token starts at q
+                    ok = ok && cb + (int32_t)q <= (int32_t)n;
+                    if (ok) ws->delta[p] = (uint16_t)(2 * (q - p));
+                }
+                __syncwarp();
+            }
+            // ---------------- the serial part: 32 dependent shared-memory reads ----------------
+            uint32_t p2 = 2 * sh;                                    // twice the chunk position = byte offset into delta[]
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                ws->pos[k] = (uint16_t)p2;
+                p2 += *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(ws->delta) + p2);
+            }
+            const uint32_t p = p2 >> 1;
+            const uint32_t mp = ws->pos[lane] >> 1;
+            const bool valid = ws->delta[mp] != 0;                   // halting is absorbing: valid lanes are a prefix
+            const uint32_t k = (uint32_t)__popc(__ballot_sync(FULL, valid));
+            if (k == 0) {
+                // the token at ip is long, near the end of the stream, or broken: one exact sequence, warp-wide
+                const uint4 r = exact_step_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
+                ip = r.x; op = r.y;
+                if (r.w == 2) { st = (int)r.z; return; }
+                if (r.w == 1) { olen = op; return; }
+                continue;
+            }
+            // ---------------- every lane decodes its own token from the staged bytes ----------------
+            uint32_t myLit = 0, myLL = 0, myML = 0;
+            if (valid) {
+                const uint32_t t = ws->bytes[mp];
+                uint32_t q = mp + 1;
+                myLL = t >> 4;
+                if (myLL == RUN_MASK) { myLL += ws->bytes[q]; q += 1; }
+                myLit = (uint32_t)(cb + (int32_t)q);
+                myML = t & ML_MASK;
+                if (myML == ML_MASK) {                               // resolved => its extension bytes are staged
+                    const uint32_t y = ws->bytes[q + myLL + 2];
+                    myML += y;
+                    if (y == 255u) myML += ws->bytes[q + myLL + 3];
+                }
+                myML += MINMATCH;
+            }
+            __syncwarp();                                            // staged bytes are dead from here (next chunk overwrites them)
+            if (!expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
+            ip = (uint32_t)(cb + (int32_t)p);
+        }
+    }
+    // the exact tier finishes the block (or decides the error) from a state where all earlier sequences are complete
+    const uint2 r = finish_exact_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
+    olen = r.x;
+    st = (int)r.y;
+}
+
+template <int MIN_CTAS, int VARIANT>
 __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in, OutSet out, const uint32_t* __restrict__ hdr,
                                                            uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
                                                            uint32_t nblocks, const uint8_t* __restrict__ dict,
                                                            uint32_t dict_len, int has_dict, uint32_t* ticket) {
+    __shared__ WarpStage stage[VARIANT == 1 ? 1 : K2_WARPS];
     const uint32_t lane = lane_id();
+    WarpStage* ws = &stage[VARIANT == 1 ? 0 : (threadIdx.x >> 5)];
+    if (VARIANT != 1) {
+        for (uint32_t i = CHUNK + lane; i < DELTA_SLOTS; i += 32) ws->delta[i] = 0;   // never written again: the walk halts there
+        __syncwarp();
+    }
     for (;;) {
         uint32_t blk = 0;
         if (lane == 0) blk = atomicAdd(ticket, 1u);
@@ -349,8 +528,10 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
             // stored block: reference src/lz4f.zig:603-608
             if (n > cap) st = ST_RAW_NO_ROOM;
             else { warp_copy<true>(dst, src, n, lane); olen = n; }
+        } else if (VARIANT == 1) {
+            decode_block_fast_v1(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, olen, st);
         } else {
-            decode_block_fast(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, olen, st);
+            decode_block_fast(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, ws, olen, st);
         }
         if (lane == 0) {
             out_len[blk] = st == ST_OK ? olen : 0u;
@@ -384,18 +565,19 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
-    // CTAs of 4 warps per SM: 10 (<= 48 registers, no spills) by default — text 5.47 -> 5.31 ms, binary 5.94 -> 5.66 ms per GiB
-    // against 8 (64 registers); 12 and 16 spill and lose (6.2 / 8.4 ms) except on stored blocks.  B2_K2_OCC picks another.
-    static int occ = 0;
-    if (!occ) { const char* e = getenv("B2_K2_OCC"); int v = e ? atoi(e) : 0; occ = (v == 8 || v == 12 || v == 16) ? v : 10; }
+    // CTAs of 4 warps per SM: 10 (<= 48 registers) by default; b2lz4_debug_tune("k2_occ") picks 8 or 12 for the occupancy
+    // experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end.
+    const int occ_t = tune().k2_occ, variant = tune().k2_variant == 1 ? 1 : 2;
+    const int occ = (occ_t == 8 || occ_t == 12) ? occ_t : 10;
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
-#define B2_K2_LAUNCH(N) k_decompress<N><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, dict_len, \
-                                                                          dict != nullptr ? 1 : 0, ticket)
-    if (occ == 16) B2_K2_LAUNCH(16);
-    else if (occ == 12) B2_K2_LAUNCH(12);
-    else if (occ == 10) B2_K2_LAUNCH(10);
-    else B2_K2_LAUNCH(8);
+#define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
+                                                                              dict_len, dict != nullptr ? 1 : 0, ticket)
+    if (variant == 1) {
+        if (occ == 12) B2_K2_LAUNCH(12, 1); else if (occ == 8) B2_K2_LAUNCH(8, 1); else B2_K2_LAUNCH(10, 1);
+    } else {
+        if (occ == 12) B2_K2_LAUNCH(12, 2); else if (occ == 8) B2_K2_LAUNCH(8, 2); else B2_K2_LAUNCH(10, 2);
+    }
 #undef B2_K2_LAUNCH
     count_launch();
     return cudaGetLastError();
