@@ -57,6 +57,26 @@ def build(force=False):
 
 
 _lib = None
+_native = False
+
+
+def prefer_native():
+    """bench.py's CPU legs: rebuild the oracle with -O3 -march=native ON THE BOX THAT RUNS IT (oracle/_native/, not
+    shipped, not tracked) and load that copy; the portable -O3 build stays the one tests use.  Returns the flags used."""
+    global _SO, _lib, _native
+    if _native:
+        return "-O3 -march=native"
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, "libb2oracle.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        srcs = [os.path.join(_HERE, f) for f in ("oracle_lz4.c", "oracle_lz4hc.c", "oracle_lz4f.c", "oracle_xxh32.c")]
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=c11", "-D_GNU_SOURCE", "-pthread", "-shared",
+                               "-o", so] + srcs + ["-lpthread"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return "-O3 (portable build; native rebuild failed)"
+    _SO, _lib, _native = so, None, True
+    return "-O3 -march=native"
 
 
 def lib():

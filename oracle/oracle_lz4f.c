@@ -339,6 +339,39 @@ static void* fc_worker(void* arg) {
     return NULL;
 }
 
+/* assembly of one wave, in parallel: record i goes to its prefix-summed position (header word, stored bytes, block
+ * checksum) — the bytes are those of the serial loop at src/lz4f.zig:406-427, only the order of the copies differs */
+typedef struct {
+    const fc_job* w; uint8_t* dst; const size_t* pos; int blockChecksum; size_t next;
+} fa_job;
+
+static void* fa_worker(void* arg) {
+    fa_job* a = (fa_job*)arg;
+    for (;;) {
+        size_t i = __atomic_fetch_add(&a->next, 1, __ATOMIC_RELAXED);
+        if (i >= a->w->nblocks) break;
+        uint8_t* d = a->dst + a->pos[i];
+        wr32(d, a->w->hw[i]);
+        memcpy(d + 4, a->w->slots + i * a->w->slotStride, a->w->actual[i]);
+        if (a->blockChecksum) wr32(d + 4 + a->w->actual[i], b2o_xxh32(d + 4, a->w->actual[i], 0));
+    }
+    return NULL;
+}
+
+/* the content checksum is one serial chain over the raw input; it does not depend on the compressed
+ * bytes, so it runs on its own thread next to the block workers */
+typedef struct { const uint8_t* src; size_t n; uint32_t sum; } cc_job;
+static void* cc_worker(void* arg) {
+    cc_job* c = (cc_job*)arg;
+    c->sum = b2o_xxh32(c->src, c->n, 0);
+    return NULL;
+}
+
+/* scratch of the multi-threaded writer, kept between calls (a fresh 256 MiB malloc costs its page faults every call) */
+static pthread_mutex_t g_scratch_mu = PTHREAD_MUTEX_INITIALIZER;
+static uint8_t* g_scratch = NULL;
+static size_t g_scratch_cap = 0;
+
 int b2o_compress_frame_mt(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, const b2o_prefs* prefs,
                           size_t* out, int nthreads) {
     b2o_prefs d;
@@ -356,17 +389,34 @@ int b2o_compress_frame_mt(const uint8_t* src, size_t n, uint8_t* dst, size_t cap
     j.src = src; j.n = n; j.blockSize = blockSize; j.level = prefs->compression_level;
     j.slotStride = b2o_compress_bound(blockSize);
     j.nblocks = nblocks;
-    /* process in waves so the scratch stays bounded (<= 256 MiB) */
+    /* process in waves so the scratch stays bounded (<= 256 MiB, or one slot per thread for 4 MiB blocks) */
     size_t wave = (256u << 20) / j.slotStride;
+    if (wave < (size_t)nthreads * 2) wave = (size_t)nthreads * 2;
     if (wave < 1) wave = 1;
     if (wave > nblocks) wave = nblocks ? nblocks : 1;
-    j.slots = (uint8_t*)malloc(wave * j.slotStride);
+    pthread_mutex_lock(&g_scratch_mu);
+    if (g_scratch_cap < wave * j.slotStride) {
+        free(g_scratch);
+        g_scratch = (uint8_t*)malloc(wave * j.slotStride);
+        g_scratch_cap = g_scratch ? wave * j.slotStride : 0;
+    }
+    j.slots = g_scratch;
     j.hw = (uint32_t*)malloc(wave * sizeof(uint32_t));
     j.actual = (size_t*)malloc(wave * sizeof(size_t));
     j.rc = (int*)malloc(wave * sizeof(int));
-    if (!j.slots || !j.hw || !j.actual || !j.rc) { free(j.slots); free(j.hw); free(j.actual); free(j.rc); return B2O_F_AllocationFailed; }
-    b2o_xxh32_state cs;
-    b2o_xxh32_init(&cs, 0);
+    size_t* pos = (size_t*)malloc(wave * sizeof(size_t));
+    if (!j.slots || !j.hw || !j.actual || !j.rc || !pos) {
+        free(j.hw); free(j.actual); free(j.rc); free(pos);
+        pthread_mutex_unlock(&g_scratch_mu);
+        return B2O_F_AllocationFailed;
+    }
+    cc_job cc = {src, n, 0};
+    pthread_t cct;
+    int cc_threaded = 0;
+    if (prefs->content_checksum == 1) {
+        if (nthreads > 1 && pthread_create(&cct, NULL, cc_worker, &cc) == 0) cc_threaded = 1;
+        else cc_worker(&cc);
+    }
     rc = B2O_OK;
     for (size_t base = 0; base < nblocks && rc == B2O_OK; base += wave) {
         size_t cnt = nblocks - base < wave ? nblocks - base : wave;
@@ -375,22 +425,19 @@ int b2o_compress_frame_mt(const uint8_t* src, size_t n, uint8_t* dst, size_t cap
         run_threads(fc_worker, &w, nthreads);
         for (size_t i = 0; i < cnt; i++) {
             if (w.rc[i]) { rc = w.rc[i]; break; }
-            size_t off = (base + i) * blockSize;
-            size_t len = n - off < blockSize ? n - off : blockSize;
-            if (prefs->content_checksum == 1) b2o_xxh32_update(&cs, src + off, len);
-            wr32(dst + dstPos, w.hw[i]);
-            memcpy(dst + dstPos + 4, w.slots + i * w.slotStride, w.actual[i]);
-            dstPos += 4 + w.actual[i];
-            if (prefs->block_checksum == 1) {
-                wr32(dst + dstPos, b2o_xxh32(dst + dstPos - w.actual[i], w.actual[i], 0));
-                dstPos += 4;
-            }
+            pos[i] = dstPos;
+            dstPos += 4 + w.actual[i] + (prefs->block_checksum == 1 ? 4 : 0);
         }
+        if (rc) break;
+        fa_job a = {&w, dst, pos, prefs->block_checksum == 1, 0};
+        run_threads(fa_worker, &a, nthreads);
     }
-    free(j.slots); free(j.hw); free(j.actual); free(j.rc);
+    if (cc_threaded) pthread_join(cct, NULL);
+    free(j.hw); free(j.actual); free(j.rc); free(pos);
+    pthread_mutex_unlock(&g_scratch_mu);
     if (rc) return rc;
     wr32(dst + dstPos, 0); dstPos += 4;
-    if (prefs->content_checksum == 1) { wr32(dst + dstPos, b2o_xxh32_final(&cs)); dstPos += 4; }
+    if (prefs->content_checksum == 1) { wr32(dst + dstPos, cc.sum); dstPos += 4; }
     *out = dstPos;
     return B2O_OK;
 }

@@ -42,6 +42,11 @@ def z():
     """The product package; the library must already be built (no silent fallback)."""
     import zig_lz4_b200
     zig_lz4_b200.lib()
+    # B2_TEST_TUNE="k1_variant=2,k2_variant=1": run the same parity tests against an experimental kernel variant
+    # (the knob is the library's b2lz4_debug_tune; the library itself never reads the environment)
+    for kv in filter(None, os.environ.get("B2_TEST_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        zig_lz4_b200.debug_tune(k, int(v))
     return zig_lz4_b200
 
 

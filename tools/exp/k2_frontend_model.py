@@ -51,34 +51,44 @@ def model(src, align):
                     B[8 * w + j] = src[a] if 0 <= a < n else 0xAA   # bytes outside the stream inside a mapped word: garbage
         D = np.zeros(SLOTS, dtype=np.int64)
         lim = isafe - cb
-        ext = []
         for p in range(CHUNK):
             if p >= lim: continue
             t = int(B[p]); hi, lo = t >> 4, t & 15
-            if hi == 15 or lo == 15: ext.append(p)
-            else: D[p] = 2 * (3 + hi)
-        for p in ext:
-            t = int(B[p]); LL = t >> 4; q = p + 1; ok = True
-            if LL == 15:
-                x = int(B[q]); ok = x != 255; LL += x; q += 1
-            q += LL + 2
-            if (t & 15) == 15:
-                lim2 = CHUNK + MARGIN - 2
-                y = int(B[q if q < lim2 else lim2]); y2 = int(B[q + 1 if q < lim2 else lim2 + 1])
-                ok = ok and q < lim2 and not (y == 255 and y2 == 255)
-                q += 2 if y == 255 else 1
-            ok = ok and cb + q <= n
-            if ok: D[p] = 2 * (q - p)
+            d = 3 + hi + (1 if lo == 15 else 0)
+            if hi == 15: d += 1 + int(B[p + 1])
+            D[p] = 2 * d
         p2 = 2 * sh; pos = []
         for k in range(32):
             pos.append(p2); p2 += int(D[p2 // 2])
+        pos.append(p2)
         assert max(pos) // 2 < SLOTS
-        valid = [D[x // 2] != 0 for x in pos]
-        k = sum(valid)
-        assert all(valid[:k]) and not any(valid[k:])
-        if k == 0:
+        live = [D[x // 2] != 0 for x in pos[:32]]
+        k = sum(live)
+        assert all(live[:k]) and not any(live[k:])
+        fields = []
+        bad = []
+        for lane in range(32):
+            if not live[lane]:
+                fields.append(None); bad.append(False); continue
+            mp = pos[lane] // 2
+            t = int(B[mp]); q = mp + 1; LL = t >> 4; bd = False
+            if LL == 15:
+                x = int(B[q]); LL += x; q += 1; bd = x == 255
+            lit = cb + q; q += LL + 2; ML = t & 15
+            if ML == 15:
+                staged = q < CHUNK + MARGIN
+                y = int(B[q if staged else 0]); ML += y; q += 1
+                bd = bd or (not staged) or y == 255
+            bd = bd or cb + q > n
+            fields.append((cb + mp, lit, LL, ML + 4)); bad.append(bd)
+        cut = any(bad)
+        if cut: k = bad.index(True)
+        ipn = cb + pos[k] // 2
+        if k:
+            events.append(("batch", fields[:k]))
+        ip = ipn
+        if cut:
             events.append(("exact", ip))
-            # one exact sequence
             t = src[ip]; q = ip + 1; LL = t >> 4
             if LL == 15:
                 while True:
@@ -93,7 +103,73 @@ def model(src, align):
                     s = src[q]; q += 1
                     if s != 255: break
             ip = q
-            continue
+        continue
+    return events, ip
+    isafe = n - SPAN
+    while ip < isafe:
+        sh = (align + ip) & 7
+        cb = ip - sh
+        B = np.zeros(CHUNK + MARGIN, dtype=np.int64)
+        for w in range(32 + MARGIN // 8):
+            if cb + 8 * w < n:
+                for j in range(8):
+                    a = cb + 8 * w + j
+                    B[8 * w + j] = src[a] if 0 <= a < n else 0xAA   # bytes outside the stream inside a mapped word: garbage
+        D = np.zeros(SLOTS, dtype=np.int64)
+        lim = isafe - cb
+        for p in range(CHUNK):
+            if p >= lim: continue
+            t = int(B[p]); hi, lo = t >> 4, t & 15
+            d = 3 + hi + (1 if lo == 15 else 0)
+            if hi == 15: d += 1 + int(B[p + 1])
+            D[p] = 2 * d
+        p2 = 2 * sh; pos = []
+        for k in range(32):
+            pos.append(p2); p2 += int(D[p2 // 2])
+        pos.append(p2)
+        assert max(pos) // 2 < SLOTS
+        live = [D[x // 2] != 0 for x in pos[:32]]
+        k = sum(live)
+        assert all(live[:k]) and not any(live[k:])
+        fields = []
+        bad = []
+        for lane in range(32):
+            if not live[lane]:
+                fields.append(None); bad.append(False); continue
+            mp = pos[lane] // 2
+            t = int(B[mp]); q = mp + 1; LL = t >> 4; bd = False
+            if LL == 15:
+                x = int(B[q]); LL += x; q += 1; bd = x == 255
+            lit = cb + q; q += LL + 2; ML = t & 15
+            if ML == 15:
+                staged = q < CHUNK + MARGIN
+                y = int(B[q if staged else 0]); ML += y; q += 1
+                bd = bd or (not staged) or y == 255
+            bd = bd or cb + q > n
+            fields.append((cb + mp, lit, LL, ML + 4)); bad.append(bd)
+        cut = any(bad)
+        if cut: k = bad.index(True)
+        ipn = cb + pos[k] // 2
+        if k:
+            events.append(("batch", fields[:k]))
+        ip = ipn
+        if cut:
+            events.append(("exact", ip))
+            t = src[ip]; q = ip + 1; LL = t >> 4
+            if LL == 15:
+                while True:
+                    s = src[q]; q += 1; LL += s
+                    if s != 255: break
+            q += LL
+            if q >= n:
+                return events, n
+            q += 2
+            if (t & 15) == 15:
+                while True:
+                    s = src[q]; q += 1
+                    if s != 255: break
+            ip = q
+        continue
         seqs = []
         for lane in range(k):
             mp = pos[lane] // 2

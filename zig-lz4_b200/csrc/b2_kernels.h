@@ -13,6 +13,7 @@ void count_launch();  // bumps the process-wide kernel launch counter (b2lz4_ker
 // environment on a launch path.
 struct Tune {
     int k1_ctas;        // K1: CTAs per SM (u16-table kernel), 1..9
+    int k1_variant;     // K1: 2 = ring variant (one CTA per SM, forward input ring fed by TMA bulk copies)
     int k2_occ;         // K2: CTAs of 4 warps per SM: 8, 10, 12
     int k2_variant;     // K2: 1 = round-1 decoder (serial token walk), else the chunked decoder
     int k3_variant;     // K3 experiments

@@ -105,7 +105,7 @@ int b2lz4_debug_tune(const char* key, int value) {
     if (!key) return -1;
     b2::Tune& t = b2::tune();
     const std::string k(key);
-    int* slot = k == "k1_ctas" ? &t.k1_ctas : k == "k2_occ" ? &t.k2_occ : k == "k2_variant" ? &t.k2_variant
+    int* slot = k == "k1_ctas" ? &t.k1_ctas : k == "k1_variant" ? &t.k1_variant : k == "k2_occ" ? &t.k2_occ : k == "k2_variant" ? &t.k2_variant
               : k == "k3_variant" ? &t.k3_variant : k == "pipe_blocks" ? &t.pipe_blocks : k == "no_pipeline" ? &t.no_pipeline
               : k == "serial_walk" ? &t.serial_walk : k == "xxh_variant" ? &t.xxh_variant : nullptr;
     if (!slot && k.rfind("spare", 0) == 0 && k.size() == 6 && k[5] >= '0' && k[5] <= '7') slot = &t.spare[k[5] - '0'];

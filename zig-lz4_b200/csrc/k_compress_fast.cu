@@ -27,11 +27,10 @@
 // Blocks are handed to warps through a global ticket so long and short blocks balance.
 #include "b2_common.cuh"
 #include "b2_kernels.h"
-#include <cstdlib>
+#include <mutex>
 
 namespace b2 {
 
-constexpr int K1_WARPS = 4;
 constexpr int HASH_ENTRIES = 4096;  // LZ4_HASH_SIZE_U32, src/lz4.zig:33
 
 __device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * HASH_MULTIPLIER) >> 20; }  // :75-77
@@ -51,6 +50,85 @@ __device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
     uint32_t A = x >> 6, B = x & 63;
     return 32u * A * (A - 1u) + B * A;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Forward input ring (K1 "ring" variant): the bytes the search windows read next are staged in shared memory by
+// TMA bulk copies (cp.async.bulk, one 128-byte line per copy, completion on an mbarrier) issued a few lines ahead,
+// so a window's first dependent access is a shared-memory read instead of an L2 round trip (the u16/u32 hash tables
+// leave the SM no L1 to speak of).  Four line slots per warp; a slot is re-armed only after its previous copy has
+// been waited for, and everything in flight is drained before the warp leaves the kernel.
+constexpr uint32_t RING_LINE = 128, RING_SLOTS = 4, RING_BYTES = RING_LINE * RING_SLOTS;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct Ring {
+    uint32_t data;      // shared-memory address of this warp's RING_BYTES (512-byte aligned)
+    uint32_t bars;      // shared-memory address of its RING_SLOTS mbarriers
+    uint32_t next;      // next line (global address >> 7) to fetch; lines [next - 4, next) are resident or in flight
+    uint32_t pending;   // bit s: slot s has a copy in flight that nobody has waited for yet
+    uint32_t parity;    // bit s: phase parity the next wait on slot s must use
+    uint64_t lo16, hi16; // the block's bytes rounded out to 16-byte granules: nothing outside is ever read
+
+    __device__ __forceinline__ void wait_slot(uint32_t s) {
+        if (pending & (1u << s)) {
+            mbar_wait(bars + 8 * s, (parity >> s) & 1u);
+            parity ^= 1u << s;
+            pending &= ~(1u << s);
+        }
+    }
+    // all lanes call; makes the lines holding global addresses [a, a + 56) readable and keeps two more coming
+    __device__ __forceinline__ void ensure(uint64_t a, uint32_t lane) {
+        const uint32_t Lb = (uint32_t)(a >> 7), Le = (uint32_t)((a + 55) >> 7);
+        if (Lb >= next || next - Lb > RING_SLOTS) next = Lb;          // block start, or the search jumped past the ring
+        const uint32_t want = Lb + RING_SLOTS;                       // never overwrite line Lb
+        while (next < want && next <= Le + 2) {
+            const uint32_t s = next & (RING_SLOTS - 1);
+            wait_slot(s);                                            // a copy skipped by a jump: retire it first
+            uint64_t g0 = (uint64_t)next << 7, g1 = g0 + RING_LINE;
+            if (g0 < lo16) g0 = lo16;
+            if (g1 > hi16) g1 = hi16;
+            if (g1 > g0) {
+                __syncwarp();                                        // every lane is done reading the line this replaces
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(bars + 8 * s, (uint32_t)(g1 - g0));
+                    bulk_load(data + (uint32_t)(g0 & (RING_BYTES - 1)), reinterpret_cast<const void*>(g0), (uint32_t)(g1 - g0),
+                              bars + 8 * s);
+                }
+                pending |= 1u << s;
+            }
+            next++;
+        }
+        wait_slot(Lb & (RING_SLOTS - 1));
+        wait_slot(Le & (RING_SLOTS - 1));
+    }
+    __device__ __forceinline__ void drain() {
+#pragma unroll
+        for (uint32_t s = 0; s < RING_SLOTS; s++) wait_slot(s);
+    }
+    // unaligned little-endian u32 at global address a (its line(s) ensured)
+    __device__ __forceinline__ uint32_t read_u32(uint64_t a) const {
+        const uint32_t o = (uint32_t)a & (RING_BYTES - 1);
+        uint32_t w0, w1;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(data + (o & ~3u)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(data + ((o + 4) & (RING_BYTES - 4))));
+        return __funnelshift_r(w0, w1, (o & 3u) * 8);
+    }
+};
 
 // 255-run length extension bytes (src/lz4.zig:368-382 / :416-429)
 __device__ __forceinline__ void write_len_ext(uint8_t* p, uint32_t L, uint32_t cnt, uint32_t lane) {
@@ -376,9 +454,9 @@ __device__ __noinline__ uint32_t search_later_windows(const uint8_t* __restrict_
     }
 }
 
-template <typename TableT>
+template <typename TableT, bool RING>
 __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
-                                  TableT* table, uint32_t lane, uint32_t& olen, int& st) {
+                                  TableT* table, uint32_t lane, uint32_t& olen, int& st, Ring& ring) {
     st = ST_OK;
     olen = 0;
     if (n == 0) return;                                          // :299
@@ -398,15 +476,22 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
         const uint32_t mlimit = n - LASTLITERALS;  // matchLimit, :314
         const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
         uint32_t e = 0;  // last put() position; the search starts at e + 1 (0: nothing put, table value 0 == empty)
+        const uint64_t ga = reinterpret_cast<uint64_t>(src);
+        if (RING) {
+            ring.lo16 = ga & ~uint64_t(15);
+            ring.hi16 = (ga + n + 15) & ~uint64_t(15);
+            ring.next = 0xFFFFFFFFu;                             // nothing of this block is resident
+        }
 
         while (e + 1 < lim) {                                    // :320 with ip == e + 1
-            if (lane == 0 && e + 512 < n) prefetch_l1(src + e + 512);
+            if (RING) ring.ensure(ga + e, lane);
+            else if (lane == 0 && e + 512 < n) prefetch_l1(src + e + 512);
             // ---------------- window: p = base + lane ----------------
             const uint32_t base = e;
             const uint32_t p = base + lane;
             const bool inwin = p <= lim;                         // positions the walk may touch (p + 3 <= n - 9)
             uint32_t v = 0, h = 0x80000000u | lane, old = 0;
-            if (inwin) { v = ld_u32x(src + p); h = hash4(v); old = table[h]; }
+            if (inwin) { v = RING ? ring.read_u32(ga + p) : ld_u32x(src + p); h = hash4(v); old = table[h]; }
             const uint32_t peers = __match_any_sync(FULL, h);
             bool vold = inwin && old > 0 && old + MAX_DISTANCE >= p;     // :345-347 (old < e <= p always)
             // One 16-byte read at the candidate serves the 4-byte compare (:348) and stages the next
@@ -434,7 +519,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             uint32_t mlpk;
             {
                 uint32_t v2 = 0;
-                if (lane < 16 && p + 32 <= lim) v2 = ld_u32x(src + p + 32);
+                if (lane < 16 && p + 32 <= lim) v2 = RING ? ring.read_u32(ga + p + 32) : ld_u32x(src + p + 32);
                 const uint32_t a1 = __shfl_sync(FULL, v, lane + 4), b1 = __shfl_sync(FULL, v2, lane + 4);
                 const uint32_t a2 = __shfl_sync(FULL, v, lane + 8), b2 = __shfl_sync(FULL, v2, lane + 8);
                 const uint32_t a3 = __shfl_sync(FULL, v, lane + 12), b3 = __shfl_sync(FULL, v2, lane + 12);
@@ -544,21 +629,38 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
     olen = total;
 }
 
-template <typename TableT>
+template <typename TableT, bool RING>
 __device__ __forceinline__ void compress_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst,
                                                uint32_t cap, TableT* table, uint32_t accel, uint32_t lane, uint32_t& olen,
-                                               int& st) {
-    if (accel <= 1) compress_block_a1<TableT>(src, n, dst, cap, table, lane, olen, st);  // :321 clamps 0 to 1
+                                               int& st, Ring& ring) {
+    if (accel <= 1) compress_block_a1<TableT, RING>(src, n, dst, cap, table, lane, olen, st, ring);  // :321 clamps 0 to 1
     else compress_block_general<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
 }
 
-template <typename TableT>
-__global__ void __launch_bounds__(96, 9) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
+// WARPS warps per CTA, CTAS CTAs per SM.  RING: one CTA per SM whose warps also own a forward input ring.
+template <typename TableT, bool RING, int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                               int32_t* __restrict__ status, uint32_t nblocks,
                                                               uint32_t accel, uint32_t* ticket) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    TableT* table = reinterpret_cast<TableT*>(smem_raw) + (threadIdx.x >> 5) * HASH_ENTRIES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5;
+    TableT* table = reinterpret_cast<TableT*>(smem_raw) + warp * HASH_ENTRIES;
     const uint32_t lane = lane_id();
+    Ring ring;
+    ring.data = ring.bars = ring.pending = ring.parity = 0;
+    ring.next = 0xFFFFFFFFu;
+    ring.lo16 = ring.hi16 = 0;
+    if (RING) {
+        uint8_t* rbase = smem_raw + (size_t)WARPS * HASH_ENTRIES * sizeof(TableT);       // multiple of 8 KiB: 512-aligned
+        ring.data = smem_addr(rbase + warp * RING_BYTES);
+        ring.bars = smem_addr(rbase + WARPS * RING_BYTES + warp * RING_SLOTS * 8);
+        if (lane == 0) {
+            for (uint32_t s = 0; s < RING_SLOTS; s++) mbar_init(ring.bars + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (;;) {
         uint32_t blk = 0;
         if (lane == 0) blk = atomicAdd(ticket, 1u);
@@ -574,13 +676,14 @@ __global__ void __launch_bounds__(96, 9) k_compress_fast(BlockSet in, OutSet out
         __builtin_assume(__isGlobal(src));
         __builtin_assume(__isGlobal(dst));
         uint32_t olen; int st;
-        compress_block<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
+        compress_block<TableT, RING>(src, n, dst, cap, table, accel, lane, olen, st, ring);
         if (lane == 0) {
             out_len[blk] = st == ST_OK ? olen : 0u;
             status[blk] = st;
         }
         __syncwarp();
     }
+    if (RING) ring.drain();   // no bulk copy may still be writing this CTA's shared memory when it exits
 }
 
 // Host launcher.  max_len decides the table entry width.
@@ -591,30 +694,44 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     const bool small = max_len <= 65536;
-    // shared memory per SM is what bounds the blocks in flight (227 KiB, 1 KiB reserved per CTA):
+    // shared memory per SM is what bounds the blocks in flight (227 KiB per CTA, 228 per SM, 1 KiB reserved per CTA):
     //   u16 tables (8 KiB / warp):  CTAs of 3 warps, 9 per SM -> 27 blocks in flight
     //   u32 tables (16 KiB / warp): CTAs of 1 warp, 13 per SM -> 13 blocks in flight
-    const int warps = small ? 3 : 1;
-    int ctas_per_sm = small ? 9 : 13;
-    if (const char* e = getenv("B2_K1_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas_per_sm) ctas_per_sm = v; }   // occupancy experiments
-    const size_t smem = (size_t)warps * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_compress_fast<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             K1_WARPS * HASH_ENTRIES * (int)sizeof(uint32_t));
-        cudaFuncSetAttribute(k_compress_fast<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             K1_WARPS * HASH_ENTRIES * (int)sizeof(uint16_t));
-        cudaFuncSetAttribute(k_compress_fast<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_compress_fast<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_done = true;
+    //   ring variant (b2lz4_debug_tune("k1_variant", 2)): ONE CTA per SM of 26 (u16) / 13 (u32) warps, each with its table,
+    //   a 512-byte forward input ring fed by TMA bulk copies and four mbarriers
+    const Tune& t = tune();
+    const bool ring = t.k1_variant == 2;
+    static std::once_flag attr_once[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(attr_once[dev & 15], [] {
+        auto set = [](const void* f, int bytes) {
+            cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        };
+        set((const void*)k_compress_fast<uint16_t, false, 3, 9>, 3 * HASH_ENTRIES * 2);
+        set((const void*)k_compress_fast<uint32_t, false, 1, 13>, HASH_ENTRIES * 4);
+        set((const void*)k_compress_fast<uint16_t, true, 26, 1>, 26 * (HASH_ENTRIES * 2 + (int)RING_BYTES + (int)RING_SLOTS * 8));
+        set((const void*)k_compress_fast<uint32_t, true, 13, 1>, 13 * (HASH_ENTRIES * 4 + (int)RING_BYTES + (int)RING_SLOTS * 8));
+    });
+    if (ring && accel <= 1) {
+        const int warps = small ? 26 : 13;
+        const size_t smem = (size_t)warps * (HASH_ENTRIES * (small ? 2 : 4) + RING_BYTES + RING_SLOTS * 8);
+        uint32_t want = (nblocks + warps - 1) / warps;
+        uint32_t grid = want < (uint32_t)num_sms ? want : (uint32_t)num_sms;
+        if (small) k_compress_fast<uint16_t, true, 26, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        else k_compress_fast<uint32_t, true, 13, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+    } else {
+        const int warps = small ? 3 : 1;
+        int ctas_per_sm = small ? 9 : 13;
+        if (t.k1_ctas > 0 && t.k1_ctas < ctas_per_sm) ctas_per_sm = t.k1_ctas;   // occupancy experiments
+        const size_t smem = (size_t)warps * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
+        uint32_t want = (nblocks + warps - 1) / warps;
+        uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
+        uint32_t grid = want < maxg ? want : maxg;
+        if (small) k_compress_fast<uint16_t, false, 3, 9><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        else k_compress_fast<uint32_t, false, 1, 13><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     }
-    uint32_t want = (nblocks + warps - 1) / warps;
-    uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
-    uint32_t grid = want < maxg ? want : maxg;
-    if (small)
-        k_compress_fast<uint16_t><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
-    else
-        k_compress_fast<uint32_t><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     count_launch();
     return cudaGetLastError();
 }

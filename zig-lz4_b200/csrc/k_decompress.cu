@@ -375,16 +375,22 @@ constexpr uint32_t DELTA_SLOTS = 544;  // the walk may stand on any position < C
 struct __align__(16) WarpStage {
     uint8_t bytes[CHUNK + CHUNK_MARGIN];
     uint16_t delta[DELTA_SLOTS];
-    uint16_t pos[32];
+    uint16_t pos[40];                  // [32] = where the walk stands after its last step
 };
 
-// Token lengths of four positions at once: bytes of `x` are candidate tokens.  d = 2 * (3 + LL) per byte (plain tokens;
-// deltas are kept doubled = as byte offsets into the u16 delta table, one add less per step of the walk);
-// e has bit 4 of a byte set when that token has a length-extension (either nibble 15), and d is cleared there.
-__device__ __forceinline__ void plain_deltas(uint32_t x, uint32_t& d, uint32_t& e) {
+// Token lengths of four positions at once, SPECULATIVELY: the bytes of `x` are candidate tokens, the bytes of `xs` the
+// byte after each.  A plain token is 3 + LL bytes long; a token with an LL extension is assumed to have exactly one
+// extension byte (19 + that byte), one with an ML extension exactly one more byte.  Whoever turns out to be a real
+// token checks its own assumption after the walk (a 255 extension byte ends the batch there).  Returns the lengths
+// doubled (= byte offsets into the u16 delta table: one add less per walk step) as two pairs of u16.
+__device__ __forceinline__ void token_deltas(uint32_t x, uint32_t xs, uint32_t keep, uint32_t& lo16, uint32_t& hi16) {
     const uint32_t hi = (x >> 4) & 0x0F0F0F0Fu, lo = x & 0x0F0F0F0Fu;
-    e = ((hi + 0x01010101u) | (lo + 0x01010101u)) & 0x10101010u;
-    d = ((hi << 1) + 0x06060606u) & ~((e >> 4) * 0xFFu);
+    const uint32_t eh = ((hi + 0x01010101u) >> 4) & 0x01010101u;   // 1 where the LL nibble is 15
+    const uint32_t el = ((lo + 0x01010101u) >> 4) & 0x01010101u;   // 1 where the ML nibble is 15
+    const uint32_t d8 = (hi + 0x03030303u + el + eh) & keep;       // <= 20 per byte
+    const uint32_t xm = xs & (eh * 0xFFu) & keep;                  // the LL extension byte where there is one
+    lo16 = (__byte_perm(d8, 0u, 0x4140) + __byte_perm(xm, 0u, 0x4140)) << 1;   // <= 2 * 275: no carry between halves
+    hi16 = (__byte_perm(d8, 0u, 0x4342) + __byte_perm(xm, 0u, 0x4342)) << 1;
 }
 
 __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
@@ -396,11 +402,12 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
     if (n == 0 || cap == 0) return;          // :97-98
     if (n > PLAIN_SPAN && n < 0x7F000000u) {   // (chunk positions are kept in int32)
         const uint32_t isafe = n - PLAIN_SPAN;   // a plain token below this reads its offset in bounds and is followed by more stream
+        int32_t cb = 0;                          // block position of chunk byte 0 (>= -7)
+        bool staged_ok = false;                  // the staged chunk still has >= 56 bytes after ip: walk it again
         while (ip < isafe) {
-            // ---------------- stage the next 256 (+32) stream bytes, 8-byte aligned ----------------
-            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src + ip) & 7);
-            const int32_t cb = (int32_t)ip - (int32_t)sh;          // block position of chunk byte 0 (>= -7)
-            {
+            if (!staged_ok) {
+                // ---------------- stage the next 256 (+32) stream bytes, 8-byte aligned ----------------
+                cb = (int32_t)ip - (int32_t)(reinterpret_cast<uintptr_t>(src + ip) & 7);
                 const uint2* g = reinterpret_cast<const uint2*>(src + cb);
                 uint2 w = make_uint2(0u, 0u);
                 if (cb + 8 * (int32_t)lane < (int32_t)n) w = __ldg(g + lane);   // a word that holds a stream byte is mapped
@@ -411,84 +418,78 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                     reinterpret_cast<uint2*>(ws->bytes)[32 + lane] = m;
                 }
                 if (lane < 4 && ip + 1024 + lane * 128 < n) prefetch_l2(src + ip + 1024 + lane * 128);
+                __syncwarp();
+                const uint32_t nx = reinterpret_cast<const uint32_t*>(ws->bytes)[2 * lane + 2];   // the 4 bytes after mine
                 // ---------------- distance to the next token from every position ----------------
-                uint32_t d0, d1, e0, e1;
-                plain_deltas(w.x, d0, e0);
-                plain_deltas(w.y, d1, e1);
+                uint32_t keep0 = 0xFFFFFFFFu, keep1 = 0xFFFFFFFFu;
                 const int32_t lim = (int32_t)isafe - cb;            // positions >= lim are left to the exact tier
                 if (lim < (int32_t)CHUNK) {
                     const int32_t kv = lim - 8 * (int32_t)lane;      // valid positions of this lane
                     const uint64_t keep = kv <= 0 ? 0ull : (kv >= 8 ? ~0ull : ((1ull << (8 * kv)) - 1ull));
-                    d0 &= (uint32_t)keep; d1 &= (uint32_t)(keep >> 32);
-                    e0 &= (uint32_t)keep; e1 &= (uint32_t)(keep >> 32);
+                    keep0 = (uint32_t)keep; keep1 = (uint32_t)(keep >> 32);
                 }
                 uint4 dd;
-                dd.x = __byte_perm(d0, 0u, 0x4140); dd.y = __byte_perm(d0, 0u, 0x4342);
-                dd.z = __byte_perm(d1, 0u, 0x4140); dd.w = __byte_perm(d1, 0u, 0x4342);
+                token_deltas(w.x, __funnelshift_r(w.x, w.y, 8), keep0, dd.x, dd.y);
+                token_deltas(w.y, __funnelshift_r(w.y, nx, 8), keep1, dd.z, dd.w);
                 reinterpret_cast<uint4*>(ws->delta)[lane] = dd;
                 __syncwarp();
-                // tokens with length-extension bytes: one LL byte and up to two ML bytes are resolved here
-                uint32_t em = (e0 >> 4) | (e1 >> 3);                 // bit 8j: position j, bit 8j+1: position 4+j
-                while (em) {
-                    const uint32_t b = (uint32_t)__ffs(em) - 1;
-                    em &= em - 1;
-                    const uint32_t p = 8 * lane + 4 * (b & 1) + (b >> 3);
-                    const uint32_t t = ws->bytes[p];
-                    uint32_t LL = t >> 4, q = p + 1;
-                    bool ok = true;
-                    if (LL == RUN_MASK) { const uint32_t x = ws->bytes[q]; ok = x != 255u; LL += x; q += 1; }
-                    q += LL + 2;                                     // past literals and offset
-                    if ((t & ML_MASK) == ML_MASK) {
-                        const uint32_t y = ws->bytes[q < CHUNK + CHUNK_MARGIN - 2 ? q : CHUNK + CHUNK_MARGIN - 2];
-                        const uint32_t y2 = ws->bytes[q < CHUNK + CHUNK_MARGIN - 2 ? q + 1 : CHUNK + CHUNK_MARGIN - 1];
-                        ok = ok && q < CHUNK + CHUNK_MARGIN - 2 && !(y == 255u && y2 == 255u);
-                        q += y == 255u ? 2 : 1;
-                    }
-                    // every byte of the token lies in the stream, and (q <= n - 2 is not needed: :146 only asks ip < iend
-                    // after the literals, which q - 2 - (ML bytes) < n gives) the next token starts at q
-                    ok = ok && cb + (int32_t)q <= (int32_t)n;
-                    if (ok) ws->delta[p] = (uint16_t)(2 * (q - p));
-                }
-                __syncwarp();
             }
-            // ---------------- the serial part: 32 dependent shared-memory reads ----------------
-            uint32_t p2 = 2 * sh;                                    // twice the chunk position = byte offset into delta[]
+            // ---------------- the serial part: up to 32 dependent shared-memory reads, in groups of 8 ----------------
+            uint32_t p2 = 2 * (uint32_t)((int32_t)ip - cb);          // twice the chunk position = byte offset into delta[]
+            uint32_t steps = 32;
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                ws->pos[k] = (uint16_t)p2;
-                p2 += *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(ws->delta) + p2);
+            for (int g8 = 0; g8 < 4; g8++) {
+                uint32_t d = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    ws->pos[g8 * 8 + k] = (uint16_t)p2;
+                    d = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(ws->delta) + p2);
+                    p2 += d;
+                }
+                if (g8 < 3 && d == 0) { steps = 8 * (g8 + 1); break; }   // the walk stands still: nothing more in this chunk
             }
-            const uint32_t p = p2 >> 1;
-            const uint32_t mp = ws->pos[lane] >> 1;
-            const bool valid = ws->delta[mp] != 0;                   // halting is absorbing: valid lanes are a prefix
-            const uint32_t k = (uint32_t)__popc(__ballot_sync(FULL, valid));
-            if (k == 0) {
-                // the token at ip is long, near the end of the stream, or broken: one exact sequence, warp-wide
+            ws->pos[32] = (uint16_t)p2;
+            // ---------------- every lane decodes its own token from the staged bytes and checks the speculation ----------------
+            const uint32_t mp = ws->pos[lane] >> 1;                  // (lanes >= steps read a stale but in-range position)
+            const bool live = lane < steps && ws->delta[mp] != 0;    // halting (chunk end / exact-tier zone) is absorbing: a prefix of lanes
+            uint32_t myLit = 0, myLL = 0, myML = 0;
+            bool bad = false;
+            if (live) {
+                const uint32_t t = ws->bytes[mp];
+                uint32_t q = mp + 1;
+                myLL = t >> 4;
+                if (myLL == RUN_MASK) { const uint32_t x = ws->bytes[q]; myLL += x; q += 1; bad = x == 255u; }
+                myLit = (uint32_t)(cb + (int32_t)q);
+                q += myLL + 2;                                       // past literals and offset
+                myML = t & ML_MASK;
+                if (myML == ML_MASK) {
+                    const bool staged = q < CHUNK + CHUNK_MARGIN;
+                    const uint32_t y = ws->bytes[staged ? q : 0u];
+                    myML += y;
+                    q += 1;
+                    bad = bad || !staged || y == 255u;
+                }
+                myML += MINMATCH;
+                bad = bad || cb + (int32_t)q > (int32_t)n;           // the whole token lies inside the stream
+            }
+            const uint32_t lm = __ballot_sync(FULL, live), bm = __ballot_sync(FULL, bad);
+            uint32_t k = (uint32_t)__popc(lm);
+            const bool cut = bm != 0;                                // a token needs the exact tier: the batch ends before it
+            if (cut) k = (uint32_t)__ffs(bm) - 1;
+            const uint32_t ipn = (uint32_t)(cb + (int32_t)(ws->pos[k] >> 1));
+            if (lane >= k) { myLL = 0; myML = 0; }
+            __syncwarp();                                            // staged bytes are dead from here (next chunk overwrites them)
+            if (k != 0 && !expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
+            ip = ipn;
+            staged_ok = (int32_t)ip - cb <= (int32_t)CHUNK - 56;
+            if (cut) {
+                // a long, broken or stream-ending token: one exact sequence, warp-wide, with the reference's checks
                 const uint4 r = exact_step_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
                 ip = r.x; op = r.y;
                 if (r.w == 2) { st = (int)r.z; return; }
                 if (r.w == 1) { olen = op; return; }
-                continue;
+                staged_ok = staged_ok && (int32_t)ip - cb <= (int32_t)CHUNK - 56;
             }
-            // ---------------- every lane decodes its own token from the staged bytes ----------------
-            uint32_t myLit = 0, myLL = 0, myML = 0;
-            if (valid) {
-                const uint32_t t = ws->bytes[mp];
-                uint32_t q = mp + 1;
-                myLL = t >> 4;
-                if (myLL == RUN_MASK) { myLL += ws->bytes[q]; q += 1; }
-                myLit = (uint32_t)(cb + (int32_t)q);
-                myML = t & ML_MASK;
-                if (myML == ML_MASK) {                               // resolved => its extension bytes are staged
-                    const uint32_t y = ws->bytes[q + myLL + 2];
-                    myML += y;
-                    if (y == 255u) myML += ws->bytes[q + myLL + 3];
-                }
-                myML += MINMATCH;
-            }
-            __syncwarp();                                            // staged bytes are dead from here (next chunk overwrites them)
-            if (!expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
-            ip = (uint32_t)(cb + (int32_t)p);
         }
     }
     // the exact tier finishes the block (or decides the error) from a state where all earlier sequences are complete
@@ -565,10 +566,10 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
-    // CTAs of 4 warps per SM: 10 (<= 48 registers) by default; b2lz4_debug_tune("k2_occ") picks 8 or 12 for the occupancy
-    // experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end.
+    // CTAs of 4 warps per SM: 8 (64 registers, no spills) by default; b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
+    // occupancy experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end (10 per SM).
     const int occ_t = tune().k2_occ, variant = tune().k2_variant == 1 ? 1 : 2;
-    const int occ = (occ_t == 8 || occ_t == 12) ? occ_t : 10;
+    const int occ = (occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
