@@ -535,7 +535,10 @@ def main():
     # N > 1: the frame is sharded by block range, one process per GPU (zig-lz4_b200/sharded.py)
     engine = sharded.CudaEngine(local) if world > 1 else None
     ctx = engine.ctx if engine else z.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library maps stream 0 to the context's own stream, and the CUDA events below
+    # must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     s = stream.cuda_stream
 
     def barrier():

@@ -90,7 +90,11 @@ B2LZ4_API int b2lz4_debug_tune(const char* key, int value);
 /* One context = one GPU + its workspace (block slots, size/offset tables, pinned staging) and a
  * private stream.  The reference has no such object (it is single-threaded CPU code, no globals —
  * SURVEY §8b "Threading"); functions without a ctx argument use a lazily created per-process
- * default context guarded by a mutex, so they stay callable from several host threads. */
+ * default context guarded by a mutex, so they stay callable from several host threads.
+ * Stream rule for the *_dev calls (asynchronous on the caller's stream): a context owns ONE set of scratch (work
+ * ticket, HC tables, dictionary table, checksum state), so the library orders every call on a context after the
+ * previous call on that context on the device — the new call's stream waits for an event recorded at the end of the
+ * previous one — whatever streams were passed.  Calls that should overlap on the device need one context each. */
 typedef struct b2lz4_ctx b2lz4_ctx;
 B2LZ4_API int b2lz4_ctx_create(int device /* -1 = current */, b2lz4_ctx** out);
 B2LZ4_API void b2lz4_ctx_destroy(b2lz4_ctx* ctx);

@@ -61,6 +61,36 @@ def test_two_ranks_gloo_frame_equals_one_shot(tmp_path, oracle):
             assert f.read() == "ok"
 
 
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (the driver's multi-GPU box; bench.py --gpus N runs the same "
+                                             "checks as a pre-flight)")
+def test_two_ranks_nccl_cuda_engine(tmp_path, z, oracle):
+    """two processes, one GPU each, NCCL, the product engine: gathered frame == the oracle's one-shot frame, sharded decode
+    == each rank's input, a corrupted content checksum raises ContentChecksumInvalid on both ranks"""
+    port, out = _free_port(), str(tmp_path / "result")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_sharded_nccl_worker.py"), str(r), "2", str(port), out],
+                              env=env) for r in range(2)]
+    try:
+        for p in procs:
+            p.wait(timeout=600)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r in range(2):
+        with open("%s.%d" % (out, r)) as f:
+            assert f.read() == "ok"
+
+
 @pytest.mark.gpu
 def test_cuda_engine_single_rank(z, oracle):
     """world_size 1 through the product engine: same frame as the one-shot call, decode through index + cuts"""

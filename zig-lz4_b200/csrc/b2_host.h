@@ -82,6 +82,11 @@ struct b2lz4_ctx {
     cudaStream_t side = nullptr;     // content-checksum chain runs here, concurrently
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pointer pipeline
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Every call that touches the context's scratch (work ticket, HC tables, dictionary table, checksum state) is
+    // ordered after the previous one on the DEVICE, whatever stream the caller passed: see b2::OrderGuard.
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
     cudaEvent_t ev_t[8] = {};
     cudaEvent_t ev_pipe[12] = {};
     std::recursive_mutex mu;
@@ -116,6 +121,26 @@ struct b2lz4_ctx {
                          reinterpret_cast<b2::DecodeSummary*>(sm + 192), x_stream[i - 1]};
     }
 };
+
+namespace b2 {
+// Held (under c->mu) by every entry point that enqueues work using the context's scratch on stream s.  Two calls on one
+// context with different streams would otherwise run concurrently on the device and trample the shared work ticket /
+// HC tables / checksum state; the guard makes s wait for the previous call's event and records a new one on exit.
+struct OrderGuard {
+    b2lz4_ctx* c;
+    cudaStream_t s;
+    OrderGuard(b2lz4_ctx* ctx, cudaStream_t stream) : c(ctx), s(stream) {
+        if (c->last_valid && c->last_stream != s) cudaStreamWaitEvent(s, c->ev_last, 0);
+    }
+    ~OrderGuard() {
+        if (cudaEventRecord(c->ev_last, s) == cudaSuccess) { c->last_stream = s; c->last_valid = true; }
+    }
+};
+// host-pointer entry points (synchronous, on the context's own streams): finish whatever an earlier asynchronous call left
+inline void wait_previous(b2lz4_ctx* c) {
+    if (c->last_valid) cudaEventSynchronize(c->ev_last);
+}
+}  // namespace b2
 
 // internal entry points shared between translation units
 int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, size_t cap, const b2lz4f_prefs* prefs,

@@ -61,7 +61,7 @@ cudaError_t launch_decoded_size(const BlockSet& in, const uint32_t* hdr, uint32_
                                 uint32_t nblocks, int num_sms, cudaStream_t stream);
 
 // K3 — HC hash-chain compressor (k_compress_hc.cu).  work: per-resident-warp tables (hc_work_bytes()).
-size_t hc_work_bytes(int num_sms);
+size_t hc_work_bytes(int num_sms, uint32_t nblocks);
 cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
                                uint32_t nblocks, int nb_searches, uint8_t* work, uint32_t* ticket, int num_sms,
                                cudaStream_t stream);

@@ -141,6 +141,7 @@ int b2lz4_ctx_create(int device, b2lz4_ctx** out) {
     }
     B2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     B2_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
     for (auto& e : c->ev_t) B2_CUDA(cudaEventCreate(&e));
     for (auto& e : c->ev_pipe) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B2_CUDA(c->small.ensure(1024));
@@ -167,6 +168,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     for (auto& e : c->ev_pipe) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
@@ -327,9 +329,11 @@ static OutSet explicit_out(void* base, const uint64_t* off, const uint32_t* cap)
 }
 
 // HC tables must start zeroed once (bucket values carry an epoch base afterwards).
-static int ensure_hc_work(b2lz4_ctx* c, cudaStream_t s) {
-    const size_t need = hc_work_bytes(c->num_sms);
+// The workspace grows with the largest launch seen (a fresh, zeroed buffer is a valid state: epoch base 0, empty tables).
+static int ensure_hc_work(b2lz4_ctx* c, cudaStream_t s, uint32_t nblocks) {
+    const size_t need = hc_work_bytes(c->num_sms, nblocks);
     if (c->hc_work.cap >= need) return B2LZ4_OK;
+    B2_CUDA(cudaStreamSynchronize(s));            // nothing in flight may still use the buffer that is about to be freed
     B2_CUDA(c->hc_work.ensure(need));
     B2_CUDA(cudaMemsetAsync(c->hc_work.p, 0, need, s));
     return B2LZ4_OK;
@@ -347,7 +351,7 @@ static int encode_blocks_to_slots(b2lz4_ctx* c, const b2_ws_ref& w, const void* 
     if (level > 0) {
         int nbs = hc_nb_searches(level);
         if (nbs < 0) return B2LZ4_ERR_UNSUPPORTED_LEVEL;
-        { int rc = ensure_hc_work(c, s); if (rc) return rc; }
+        { int rc = ensure_hc_work(c, s, nb); if (rc) return rc; }
         B2_CUDA(launch_compress_hc(in, out, w.csize->as<uint32_t>(), w.status->as<int32_t>(), nb, nbs,
                                    c->hc_work.as<uint8_t>(), w.ticket, c->num_sms, s));
     } else {
@@ -389,6 +393,7 @@ int b2_compress_dev_impl(b2lz4_ctx* c, const void* src, size_t n, void* dst, siz
     *out = 0;
     if (!s) s = c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     size_t bs;
     const bool bs_ok = block_size_of(prefs->block_size_id, bs);
@@ -587,6 +592,7 @@ int b2_decompress_dev_impl(b2lz4_ctx* c, const void* srcv, size_t n, void* dstv,
     *out = 0;
     if (!s) s = c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     const uint8_t* src = (const uint8_t*)srcv;
     uint8_t* dst = (uint8_t*)dstv;
@@ -661,6 +667,7 @@ int b2lz4f_decompress_blocks_dev(b2lz4_ctx* c, const void* srcv, size_t n, void*
     *out = 0;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     const uint8_t* src = (const uint8_t*)srcv;
     Timer T{c, s, c->timing};
@@ -692,6 +699,7 @@ int b2lz4f_index_frame_dev(b2lz4_ctx* c, const void* srcv, size_t n, uint64_t* o
     memset(info, 0, sizeof *info);
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     const uint8_t* src = (const uint8_t*)srcv;
     uint8_t hb[32];
@@ -726,6 +734,7 @@ int b2lz4_compress_fast_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t*
     if (nblocks > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     // block lengths live on the device: use the wide (u32) hash table, valid for every block size
     B2_CUDA(launch_compress_fast(explicit_in(src, src_off, src_len), explicit_out(dst, dst_off, dst_cap), out_len, status,
@@ -740,6 +749,7 @@ int b2lz4_compress_fast_dict_batch_dev(b2lz4_ctx* c, const void* src, const uint
     if (nblocks > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     B2_CUDA(c->dict_table.ensure(4096 * 4));
     B2_CUDA(launch_compress_fast_dict(explicit_in(src, src_off, src_len), explicit_out(dst, dst_off, dst_cap), out_len, status,
@@ -755,6 +765,7 @@ int b2lz4_decompress_safe_batch_dev(b2lz4_ctx* c, const void* src, const uint64_
     if (nblocks > 0x7FFFFFFFull || dict_len > 0xFFFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     B2_CUDA(launch_decompress(explicit_in(src, src_off, src_len), explicit_out(dst, dst_off, dst_cap), nullptr, out_len, status,
                               (uint32_t)nblocks, (const uint8_t*)dict, (uint32_t)dict_len, c->d_ticket(), c->num_sms, s));
@@ -770,8 +781,9 @@ int b2lz4_compress_hc_batch_dev(b2lz4_ctx* c, const void* src, const uint64_t* s
     if (nbs < 0) return B2LZ4_ERR_UNSUPPORTED_LEVEL;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
-    { int rc = ensure_hc_work(c, s); if (rc) return rc; }
+    { int rc = ensure_hc_work(c, s, (uint32_t)nblocks); if (rc) return rc; }
     B2_CUDA(launch_compress_hc(explicit_in(src, src_off, src_len), explicit_out(dst, dst_off, dst_cap), out_len, status,
                                (uint32_t)nblocks, nbs, c->hc_work.as<uint8_t>(), c->d_ticket(), c->num_sms, s));
     return B2LZ4_OK;
@@ -817,6 +829,7 @@ int b2lz4_compress_dest_size_batch_dev(b2lz4_ctx* c, const void* src, const uint
     if (nblocks > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     return dest_size_dev(c, src, src_off, src_len, dst, dst_off, dst_cap, consumed, out_len, status, nblocks, max_src_len, s);
 }
@@ -825,6 +838,7 @@ int b2lz4_xxh32_dev(b2lz4_ctx* c, const void* src, size_t n, uint32_t seed, uint
     if (!c || !out_dev) return B2LZ4F_ERR_PARAMETER_NULL;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     B2_CUDA(launch_xxh32_init(c->d_xxh(), seed, s));
     B2_CUDA(launch_xxh32_update(c->d_xxh(), (const uint8_t*)src, n, s));
@@ -848,6 +862,7 @@ static int host_batch(b2lz4_ctx* c, Op op, int param, const void* srcv, const ui
     if (nb == 0) return B2LZ4_OK;
     if (nb > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
@@ -892,7 +907,7 @@ static int host_batch(b2lz4_ctx* c, Op op, int param, const void* srcv, const ui
         B2_CUDA(launch_decompress(in, out, nullptr, d_olen, d_stat, (uint32_t)nb, dict ? d_dict : nullptr, (uint32_t)dict_len,
                                   c->d_ticket(), c->num_sms, s));
     } else {
-        { int rc = ensure_hc_work(c, s); if (rc) return rc; }
+        { int rc = ensure_hc_work(c, s, (uint32_t)nb); if (rc) return rc; }
         B2_CUDA(launch_compress_hc(in, out, d_olen, d_stat, (uint32_t)nb, param, c->hc_work.as<uint8_t>(), c->d_ticket(),
                                    c->num_sms, s));
     }
@@ -928,6 +943,7 @@ static int host_dest_size_batch(b2lz4_ctx* c, const void* srcv, const uint64_t* 
     if (nb == 0) return B2LZ4_OK;
     if (nb > 0x7FFFFFFFull) return B2LZ4_ERR_INPUT_TOO_LARGE;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
@@ -1071,6 +1087,7 @@ int b2lz4_xxh32(const void* src, size_t n, uint32_t seed, uint32_t* out) {
     if (!out) return B2LZ4F_ERR_PARAMETER_NULL;
     b2lz4_ctx* c; int rc = b2_default_ctx(&c); if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     B2_CUDA(c->stage_in[0].ensure(n + 16));
@@ -1095,6 +1112,7 @@ int b2lz4_xxh32_state_update_dev(b2lz4_ctx* c, b2lz4_xxh32_state* st, const void
     if (!c || !st) return B2LZ4F_ERR_PARAMETER_NULL;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    OrderGuard og(c, s);
     B2_CUDA(cudaSetDevice(c->device));
     XxhState& x = c->h()->xxh;
     for (int i = 0; i < 4; i++) { x.v[i] = st->v[i]; x.tail[i] = rd32h(st->tail + 4 * i); }

@@ -370,6 +370,7 @@ int b2lz4f_compress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* dst
     const size_t bound = b2lz4f_compress_frame_bound(n, prefs);
     if (cap < bound) return B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL;   // src/lz4f.zig:363-366
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     size_t bs;
     const int level = prefs->compression_level;
@@ -383,6 +384,7 @@ int b2lz4f_decompress_frame_ctx(b2lz4_ctx* c, const void* src, size_t n, void* d
     if (!c || !out) return B2LZ4F_ERR_PARAMETER_NULL;
     *out = 0;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     if (n > (1u << 20) && src && dst) {
         int rc = B2LZ4_OK;
@@ -503,6 +505,7 @@ int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap,
         int rc = mgpu_ctx(j.dev, &j.c); if (rc) return rc;
         b2lz4_ctx* c = j.c;
         std::lock_guard<std::recursive_mutex> lk(c->mu);
+        b2::wait_previous(c);
         B2_CUDA(cudaSetDevice(c->device));
         B2_CUDA(c->stage_in[0].ensure(j.in_len + 16));
         B2_CUDA(c->stage_out[0].ensure(j.out_cap + 16));
@@ -521,6 +524,7 @@ int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap,
     mgpu_run(jobs, [&](MgpuJob& j) -> int {
         b2lz4_ctx* c = j.c;
         std::lock_guard<std::recursive_mutex> lk(c->mu);
+        b2::wait_previous(c);
         B2_CUDA(cudaSetDevice(c->device));
         int rc = download(c, (uint8_t*)dst + j.out_off, c->stage_out[0].p, j.produced, c->stream); if (rc) return rc;
         B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -579,6 +583,7 @@ int b2lz4f_decompress_frame_mgpu(const void* srcv, size_t n, void* dst, size_t c
         int rc = mgpu_ctx(j.dev, &j.c); if (rc) return rc;
         b2lz4_ctx* c = j.c;
         std::lock_guard<std::recursive_mutex> lk(c->mu);
+        b2::wait_previous(c);
         B2_CUDA(cudaSetDevice(c->device));
         B2_CUDA(c->stage_in[0].ensure(j.in_len + 32));
         B2_CUDA(c->stage_out[0].ensure(j.out_cap + 16));
@@ -628,6 +633,7 @@ static int emit_blocks(b2lz4f_cctx* cc, const uint8_t* h_a, size_t na, const uin
     const size_t need = nblocks * (4 + compress_bound(cc->bs) + (cc->prefs.block_checksum == 1 ? 4 : 0));
     if (cap < need) return B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    b2::wait_previous(c);
     B2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     B2_CUDA(c->stage_in[0].ensure(n + 16));

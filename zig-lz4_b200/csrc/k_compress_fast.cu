@@ -76,13 +76,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 struct Ring {
-    uint32_t data;      // shared-memory address of this warp's RING_BYTES (512-byte aligned)
+    uint32_t data;      // shared-memory address of this warp's RING_BYTES
     uint32_t bars;      // shared-memory address of its RING_SLOTS mbarriers
-    uint32_t next;      // next line (global address >> 7) to fetch; lines [next - 4, next) are resident or in flight
+    uint32_t next;      // next line to fetch, counted from `line0`; lines [next - 4, next) are resident or in flight
     uint32_t pending;   // bit s: slot s has a copy in flight that nobody has waited for yet
     uint32_t parity;    // bit s: phase parity the next wait on slot s must use
+    uint64_t line0;     // global address of the 128-byte line that holds the block's first byte
     uint64_t lo16, hi16; // the block's bytes rounded out to 16-byte granules: nothing outside is ever read
 
+    __device__ __forceinline__ void begin_block(uint64_t ga, uint32_t n) {
+        line0 = ga & ~uint64_t(RING_LINE - 1);
+        lo16 = ga & ~uint64_t(15);
+        hi16 = (ga + n + 15) & ~uint64_t(15);
+        next = 0;                                                    // nothing of this block is resident
+    }
+    // slot of line L: its global address picks it, so that a byte's place in the ring is (address & 511)
+    __device__ __forceinline__ uint32_t slot_of(uint32_t L) const { return ((uint32_t)(line0 >> 7) + L) & (RING_SLOTS - 1); }
     __device__ __forceinline__ void wait_slot(uint32_t s) {
         if (pending & (1u << s)) {
             mbar_wait(bars + 8 * s, (parity >> s) & 1u);
@@ -92,13 +101,13 @@ struct Ring {
     }
     // all lanes call; makes the lines holding global addresses [a, a + 56) readable and keeps two more coming
     __device__ __forceinline__ void ensure(uint64_t a, uint32_t lane) {
-        const uint32_t Lb = (uint32_t)(a >> 7), Le = (uint32_t)((a + 55) >> 7);
+        const uint32_t Lb = (uint32_t)((a - line0) >> 7), Le = (uint32_t)((a + 55 - line0) >> 7);
         if (Lb >= next || next - Lb > RING_SLOTS) next = Lb;          // block start, or the search jumped past the ring
         const uint32_t want = Lb + RING_SLOTS;                       // never overwrite line Lb
         while (next < want && next <= Le + 2) {
-            const uint32_t s = next & (RING_SLOTS - 1);
+            const uint32_t s = slot_of(next);
             wait_slot(s);                                            // a copy skipped by a jump: retire it first
-            uint64_t g0 = (uint64_t)next << 7, g1 = g0 + RING_LINE;
+            uint64_t g0 = line0 + ((uint64_t)next << 7), g1 = g0 + RING_LINE;
             if (g0 < lo16) g0 = lo16;
             if (g1 > hi16) g1 = hi16;
             if (g1 > g0) {
@@ -113,8 +122,8 @@ struct Ring {
             }
             next++;
         }
-        wait_slot(Lb & (RING_SLOTS - 1));
-        wait_slot(Le & (RING_SLOTS - 1));
+        wait_slot(slot_of(Lb));
+        wait_slot(slot_of(Le));
     }
     __device__ __forceinline__ void drain() {
 #pragma unroll
@@ -477,11 +486,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
         const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
         uint32_t e = 0;  // last put() position; the search starts at e + 1 (0: nothing put, table value 0 == empty)
         const uint64_t ga = reinterpret_cast<uint64_t>(src);
-        if (RING) {
-            ring.lo16 = ga & ~uint64_t(15);
-            ring.hi16 = (ga + n + 15) & ~uint64_t(15);
-            ring.next = 0xFFFFFFFFu;                             // nothing of this block is resident
-        }
+        if (RING) ring.begin_block(ga, n);
 
         while (e + 1 < lim) {                                    // :320 with ip == e + 1
             if (RING) ring.ensure(ga + e, lane);
@@ -647,9 +652,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_compress_fast(BlockSet in,
     TableT* table = reinterpret_cast<TableT*>(smem_raw) + warp * HASH_ENTRIES;
     const uint32_t lane = lane_id();
     Ring ring;
-    ring.data = ring.bars = ring.pending = ring.parity = 0;
-    ring.next = 0xFFFFFFFFu;
-    ring.lo16 = ring.hi16 = 0;
+    ring.data = ring.bars = ring.pending = ring.parity = ring.next = 0;
+    ring.line0 = ring.lo16 = ring.hi16 = 0;
     if (RING) {
         uint8_t* rbase = smem_raw + (size_t)WARPS * HASH_ENTRIES * sizeof(TableT);       // multiple of 8 KiB: 512-aligned
         ring.data = smem_addr(rbase + warp * RING_BYTES);

@@ -45,7 +45,12 @@ struct HcWork {
     uint32_t pad[15];
 };
 
-size_t hc_work_bytes(int num_sms) { return (size_t)num_sms * HC_CTAS_PER_SM * HC_WARPS * sizeof(HcWork); }
+// one HcWork (256 KiB of tables) per warp that a launch over `nblocks` blocks can have in flight — not per resident
+// warp of the device: a single small block needs 1 MiB, not 2.5 GB
+size_t hc_work_bytes(int num_sms, uint32_t nblocks) {
+    const size_t ctas = (nblocks + HC_WARPS - 1) / HC_WARPS, max_ctas = (size_t)num_sms * HC_CTAS_PER_SM;
+    return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * sizeof(HcWork);
+}
 
 __device__ __forceinline__ uint32_t hashHC(uint32_t v) { return (v * HASH_MULTIPLIER) >> 17; }  // :129-131
 

@@ -306,11 +306,12 @@ __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, ui
     return true;
 }
 
-// Round-1 front end (kept for A/B runs, b2lz4_debug_tune("k2_variant", 1)): the warp walks the token chain itself.
+// Serial front end: the warp walks the token chain itself, one token per step, every kind of length extension
+// handled in place.  It is the round-1 decoder (b2lz4_debug_tune("k2_variant", 1) selects it for A/B runs) and the
+// chunked decoder's fallback for streams whose tokens keep defeating its speculation (long runs: 255-extended lengths).
 __device__ void decode_block_fast_v1(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
                                      const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
-                                     uint32_t& olen, int& st) {
-    uint32_t ip = 0, op = 0;
+                                     uint32_t ip, uint32_t op, uint32_t& olen, int& st) {
     if (n > PLAIN_SPAN && cap > 0) {
         const uint32_t iend = n;
         const uint32_t isafe = n - PLAIN_SPAN;  // plain tokens below this read in bounds without checks
@@ -368,6 +369,15 @@ __device__ __noinline__ uint2 finish_exact_ool(const uint8_t* __restrict__ src, 
     return make_uint2(olen, (uint32_t)st);
 }
 
+__device__ __noinline__ uint2 fast_v1_ool(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
+                                          const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+                                          uint32_t ip, uint32_t op) {
+    uint32_t olen = 0;
+    int st = ST_OK;
+    decode_block_fast_v1(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op, olen, st);
+    return make_uint2(olen, (uint32_t)st);
+}
+
 // ---- chunked front end ----
 constexpr uint32_t CHUNK = 256;        // stream bytes whose token lengths are computed at once (8 per lane)
 constexpr uint32_t CHUNK_MARGIN = 32;  // staged bytes after the chunk: length-extension bytes of its last tokens
@@ -404,7 +414,16 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
         const uint32_t isafe = n - PLAIN_SPAN;   // a plain token below this reads its offset in bounds and is followed by more stream
         int32_t cb = 0;                          // block position of chunk byte 0 (>= -7)
         bool staged_ok = false;                  // the staged chunk still has >= 56 bytes after ip: walk it again
+        uint32_t nbatch = 0, ncut = 0;           // batches so far / batches cut short by a token the speculation missed
         while (ip < isafe) {
+            if (nbatch >= 4 && ncut * 4 > nbatch) {
+                // every few tokens one with a 255-extended length (runs, long matches): the serial walk handles those in
+                // place and keeps 32 sequences per batch — better than cutting the batch at each of them
+                const uint2 r = fast_v1_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
+                olen = r.x;
+                st = (int)r.y;
+                return;
+            }
             if (!staged_ok) {
                 // ---------------- stage the next 256 (+32) stream bytes, 8-byte aligned ----------------
                 cb = (int32_t)ip - (int32_t)(reinterpret_cast<uintptr_t>(src + ip) & 7);
@@ -482,7 +501,9 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
             if (k != 0 && !expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
             ip = ipn;
             staged_ok = (int32_t)ip - cb <= (int32_t)CHUNK - 56;
+            nbatch++;
             if (cut) {
+                ncut++;
                 // a long, broken or stream-ending token: one exact sequence, warp-wide, with the reference's checks
                 const uint4 r = exact_step_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
                 ip = r.x; op = r.y;
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
             if (n > cap) st = ST_RAW_NO_ROOM;
             else { warp_copy<true>(dst, src, n, lane); olen = n; }
         } else if (VARIANT == 1) {
-            decode_block_fast_v1(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, olen, st);
+            decode_block_fast_v1(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, 0, 0, olen, st);
         } else {
             decode_block_fast(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, ws, olen, st);
         }
@@ -569,7 +590,7 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     // CTAs of 4 warps per SM: 8 (64 registers, no spills) by default; b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
     // occupancy experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end (10 per SM).
     const int occ_t = tune().k2_occ, variant = tune().k2_variant == 1 ? 1 : 2;
-    const int occ = (occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
+    const int occ = (occ_t == 8 || occ_t == 9 || occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
@@ -577,7 +598,8 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     if (variant == 1) {
         if (occ == 12) B2_K2_LAUNCH(12, 1); else if (occ == 8) B2_K2_LAUNCH(8, 1); else B2_K2_LAUNCH(10, 1);
     } else {
-        if (occ == 12) B2_K2_LAUNCH(12, 2); else if (occ == 8) B2_K2_LAUNCH(8, 2); else B2_K2_LAUNCH(10, 2);
+        if (occ == 12) B2_K2_LAUNCH(12, 2); else if (occ == 10) B2_K2_LAUNCH(10, 2); else if (occ == 9) B2_K2_LAUNCH(9, 2);
+        else B2_K2_LAUNCH(8, 2);
     }
 #undef B2_K2_LAUNCH
     count_launch();
