@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include "../../include/b2lz4.h"
 #include "b2_kernels.h"
+#include "b2_mover.h"
 
 namespace b2 {
 
@@ -102,6 +103,7 @@ struct b2lz4_ctx {
     b2::DevBuf x_slots[2], x_csize[2], x_status[2], x_sums[2], x_rec_off[2], x_small[2];
     cudaStream_t x_stream[2] = {nullptr, nullptr};
     b2::PinBuf results, pin_aux;
+    b2::HostMover mover;                       // pinned bounce rings + copy threads for pageable caller buffers
     // layout of `small` (device): ticket u32 @0, FrameTotals @64, WalkResult @128, DecodeSummary @192,
     // content_sum u32 @256, XxhState @320, index node count u64 @512
     uint32_t* d_ticket() const { return small.as<uint32_t>(); }

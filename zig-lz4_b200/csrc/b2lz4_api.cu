@@ -162,6 +162,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
                       &c->x_slots[0], &c->x_slots[1], &c->x_csize[0], &c->x_csize[1], &c->x_status[0], &c->x_status[1],
                       &c->x_sums[0], &c->x_sums[1], &c->x_rec_off[0], &c->x_rec_off[1], &c->x_small[0], &c->x_small[1]};
     for (auto* b : bufs) b->release();
+    c->mover.release();
     c->results.release();
     c->pin_aux.release();
     for (auto& e : c->ev_t) if (e) cudaEventDestroy(e);

@@ -31,7 +31,11 @@ static size_t compress_bound(size_t n) { return n > LZ4_MAX_INPUT_SIZE ? 0 : n +
 // itself in both directions; the codec runs once over the resident buffer.
 constexpr size_t COPY_CHUNK = 64u << 20;
 
+// Ordinary (pageable) caller memory goes through the context's pinned bounce rings (b2_mover.h); for a download the
+// bytes are in `h` only after c->mover.flush().
 static int upload(b2lz4_ctx* c, void* d, const void* h, size_t n, cudaStream_t s) {
+    if (n == 0) return B2LZ4_OK;
+    if (b2::HostMover::pageable(h)) { B2_CUDA(c->mover.h2d(d, h, n, s, true)); return B2LZ4_OK; }
     const uint8_t* hp = (const uint8_t*)h;
     uint8_t* dp = (uint8_t*)d;
     for (size_t o = 0; o < n; o += COPY_CHUNK) {
@@ -41,6 +45,8 @@ static int upload(b2lz4_ctx* c, void* d, const void* h, size_t n, cudaStream_t s
     return B2LZ4_OK;
 }
 static int download(b2lz4_ctx* c, void* h, const void* d, size_t n, cudaStream_t s) {
+    if (n == 0) return B2LZ4_OK;
+    if (b2::HostMover::pageable(h)) { B2_CUDA(c->mover.d2h(h, d, n, s, true)); return B2LZ4_OK; }
     uint8_t* hp = (uint8_t*)h;
     const uint8_t* dp = (const uint8_t*)d;
     for (size_t o = 0; o < n; o += COPY_CHUNK) {
@@ -64,8 +70,9 @@ static int compress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void* 
     rc = b2_compress_dev_impl(c, c->stage_in[0].p, n, c->stage_out[0].p, bound, prefs, &produced, s, false);
     if (rc) return rc;
     rc = download(c, dst, c->stage_out[0].p, produced, s);
-    if (rc) return rc;
+    if (rc) { c->mover.abandon(); return rc; }
     B2_CUDA(cudaStreamSynchronize(s));
+    B2_CUDA(c->mover.flush());
     *out = produced;
     return B2LZ4_OK;
 }
@@ -80,8 +87,9 @@ static int decompress_frame_simple(b2lz4_ctx* c, const void* src, size_t n, void
     rc = b2_decompress_dev_impl(c, c->stage_in[0].p, n, c->stage_out[0].p, cap, &produced, s);
     if (rc) return rc;
     rc = download(c, dst, c->stage_out[0].p, produced, s);
-    if (rc) return rc;
+    if (rc) { c->mover.abandon(); return rc; }
     B2_CUDA(cudaStreamSynchronize(s));
+    B2_CUDA(c->mover.flush());
     *out = produced;
     return B2LZ4_OK;
 }
@@ -137,6 +145,7 @@ static std::vector<size_t> chunk_plan(size_t nb, size_t chunk_blocks, bool ramp_
 constexpr int PIPE_DEPTH = 3;   // chunks in flight: staging buffers, workspaces and compute streams
 
 static void pipe_drain(b2lz4_ctx* c) {
+    c->mover.abandon();
     cudaStreamSynchronize(c->stream);
     for (auto xs : c->x_stream) cudaStreamSynchronize(xs);
     cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->copy_out); cudaStreamSynchronize(c->side);
@@ -146,6 +155,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
                                     const b2lz4f_prefs* prefs, size_t bs, size_t chunk_blocks, size_t* out) {
     const bool bc = prefs->block_checksum == 1, cc = prefs->content_checksum == 1;
     const int level = prefs->compression_level;
+    const bool page_src = b2::HostMover::pageable(src), page_dst = b2::HostMover::pageable(dst);
     size_t hsize = 0;
     { int rc = b2lz4f_write_frame_header(dst, cap, prefs, &hsize); if (rc) return rc; }      // src/lz4f.zig:369
     const size_t chunk = chunk_blocks * bs;
@@ -180,7 +190,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
                 if (cc) B2_CUDA(cudaStreamWaitEvent(c->copy_in, ev_cc[b], 0));
                 B2_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
             }
-            B2_CUDA(cudaMemcpyAsync(c->stage_in[b].p, src + o, len, cudaMemcpyHostToDevice, c->copy_in));
+            B2_CUDA(c->mover.h2d(c->stage_in[b].p, src + o, len, c->copy_in, page_src));
             B2_CUDA(cudaEventRecord(ev_up[b], c->copy_in));
             B2_CUDA(cudaStreamWaitEvent(s, ev_up[b], 0));
             if (cc) {                                        // serial content chain, chunk after chunk
@@ -202,7 +212,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
                 err = t.bad_status == B2LZ4_ERR_OUTPUT_TOO_SMALL ? B2LZ4F_ERR_DST_MAX_SIZE_TOO_SMALL : B2LZ4F_ERR_GENERIC;
                 break;
             }
-            B2_CUDA(cudaMemcpyAsync(dst + pos, c->stage_out[b].p, t.body_bytes, cudaMemcpyDeviceToHost, c->copy_out));
+            B2_CUDA(c->mover.d2h(dst + pos, c->stage_out[b].p, t.body_bytes, c->copy_out, page_dst));
             B2_CUDA(cudaEventRecord(ev_down[b], c->copy_out));
             pos += t.body_bytes;
         }
@@ -214,6 +224,7 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
         B2_CUDA(cudaStreamSynchronize(c->side));
     }
     B2_CUDA(cudaStreamSynchronize(c->copy_out));
+    B2_CUDA(c->mover.flush());
     dst[pos] = dst[pos + 1] = dst[pos + 2] = dst[pos + 3] = 0;                                  // end mark, :433
     pos += 4;
     if (cc) {                                                                                    // :437-441
@@ -233,6 +244,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
     b2lz4f_prefs info; size_t hsize = 0;
     if (b2lz4f_parse_frame_header(src, n, &info, &hsize) != B2LZ4_OK) return 0;
     size_t bs; if (!block_size_of(info.block_size_id, bs)) return 0;
+    const bool page_src = b2::HostMover::pageable(src), page_dst = b2::HostMover::pageable(dst);
     const bool bc = info.block_checksum == 1, cc = info.content_checksum == 1;
     const size_t tr = bc ? 4 : 0;
     // block index: the header chain read straight from the caller's (host) frame, src/lz4f.zig:563-591
@@ -305,7 +317,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
                 PIPE_CUDA(cudaStreamWaitEvent(s, ev_down[b], 0));
                 if (cc) PIPE_CUDA(cudaStreamWaitEvent(s, ev_cc[b], 0));
             }
-            PIPE_CUDA(cudaMemcpyAsync(c->stage_in[b].p, src + lo, in_len, cudaMemcpyHostToDevice, c->copy_in));
+            PIPE_CUDA(c->mover.h2d(c->stage_in[b].p, src + lo, in_len, c->copy_in, page_src));
             PIPE_CUDA(cudaEventRecord(ev_up[b], c->copy_in));                 // also covers the index upload (same stream)
             PIPE_CUDA(cudaStreamWaitEvent(s, ev_up[b], 0));
             const uint64_t* d_off = c->walk_off.as<uint64_t>() + i0;
@@ -339,7 +351,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
                 PIPE_CUDA(launch_xxh32_update(c->d_xxh(), c->stage_out[b].as<uint8_t>(), sm.total, c->side));
                 PIPE_CUDA(cudaEventRecord(ev_cc[b], c->side));
             }
-            PIPE_CUDA(cudaMemcpyAsync(dst + cfirst[kk] * bs, c->stage_out[b].p, sm.total, cudaMemcpyDeviceToHost, c->copy_out));
+            PIPE_CUDA(c->mover.d2h(dst + cfirst[kk] * bs, c->stage_out[b].p, sm.total, c->copy_out, page_dst));
             PIPE_CUDA(cudaEventRecord(ev_down[b], c->copy_out));
             total = cfirst[kk] * bs + sm.total;
         }
@@ -351,6 +363,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
         PIPE_CUDA(cudaStreamSynchronize(c->side));
     }
     PIPE_CUDA(cudaStreamSynchronize(c->copy_out));
+    PIPE_CUDA(c->mover.flush());
     pipe_drain(c);
 #undef PIPE_CUDA
     if (cc && rd32(src + p) != c->h()->content_sum) { *rc_out = B2LZ4F_ERR_CONTENT_CHECKSUM_INVALID; return 1; }   // :625-635
