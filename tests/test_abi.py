@@ -96,3 +96,33 @@ def test_compute_fails_loudly_without_gpu(z):
         z.lz4f.compressFrame(b"x" * 100)
     with pytest.raises(z.B2Error):
         z.Context(0)
+
+
+def _build_abi_check(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(ROOT, "zig-lz4_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "abi_check.c"), "-o", exe,
+                           "-L", libdir, "-l:libb2lz4.so", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_header_compiles_as_c_and_calls_fail_loudly_without_gpu(z, tmp_path):
+    """include/b2lz4.h through a C compiler (-Wall -Wextra -Werror): the prototypes the Zig shim binds are checked by
+    gcc, not only resolved by name; without a device every compute call returns B2LZ4_ERR_CUDA."""
+    import subprocess
+    import torch
+    exe = _build_abi_check(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == ("abi ok gpu" if torch.cuda.is_available() else "abi ok nogpu")
+
+
+@pytest.mark.gpu
+def test_c_program_round_trips_on_gpu(z, tmp_path):
+    import subprocess
+    exe = _build_abi_check(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "abi ok gpu"

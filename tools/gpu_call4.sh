@@ -41,3 +41,8 @@ ncu -i $O.k1ring.ncu-rep --page raw --csv > $O.k1ring_raw.csv 2>> $O.ncu.log
 python profiles/ncu_lines.py $O.k1ring_source.csv 40 > $O.k1ring_lines.txt 2>&1
 head -30 $O.k1ring_lines.txt
 rm -f $O.k1ring.ncu-rep
+# K3 occupancy curve (CTAs of 4 warps per SM capped): does keeping the tables inside L2 pay?
+for t in "k3_variant=1" "k3_variant=2" "k3_variant=4" "k3_variant=8" ""; do
+  timeout 300 python tools/hc_probe.py --mib 1024 --mode 0 --reps 2 --tune "$t" >> $O.k3curve.jsonl 2>> $O.k3.err
+done
+cat $O.k3curve.jsonl

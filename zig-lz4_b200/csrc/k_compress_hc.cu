@@ -292,7 +292,15 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     const uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
-    const uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
+    uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
+    const int cap_ctas = tune().k3_variant;                 // experiment: at most this many CTAs (of 4 warps) per SM
+    if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
+        const uint32_t g = (uint32_t)(num_sms * cap_ctas);
+        k_compress_hc<HC_CTAS_PER_SM_FEW><<<want < g ? want : g, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
+                                                                                 reinterpret_cast<HcWork*>(work), ticket);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (want <= few) {
         k_compress_hc<HC_CTAS_PER_SM_FEW><<<want, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
                                                                               reinterpret_cast<HcWork*>(work), ticket);
