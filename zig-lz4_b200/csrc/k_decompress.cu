@@ -257,12 +257,48 @@ __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, ui
             const bool go = pending && (pm & dep) == 0;
             uint8_t* md = dst + ms;
             const uint8_t* msrc = dst + s;
-            {   // 8 bytes at a time: all loads of a chunk are issued before its stores.  Safe for a
-                // self-overlapping match with offset >= 8: a chunk only reads bytes of earlier chunks.
-                const uint32_t nm = (go && !lng && !tiny) ? myML : 0u;
+            {   // Non-overlapping short matches (offset >= length, the common case): the whole source, up to 24 bytes, is
+                // read at once as up to four aligned 8-byte words (one memory round trip for the round instead of one
+                // per 8 bytes — these reads go to L2 or DRAM, the output of 4700 warps does not fit any cache), realigned
+                // in registers, and stored byte by byte.  Words may hold bytes around the source range (not yet written
+                // or another sequence's): they are never stored.
+                const bool wide = go && !lng && off >= myML;
+                const uint32_t nw = wide ? myML : 0u;
+                const uint32_t mxw = __reduce_max_sync(FULL, nw);
+                if (mxw) {
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(msrc) & 7);
+                    const uint2* wp = reinterpret_cast<const uint2*>(msrc - sh);
+                    const uint32_t nwords = wide ? (sh + myML + 7) >> 3 : 0u;     // 1..4
+                    uint2 A = make_uint2(0u, 0u), B = A, C = A, D = A;
+                    if (nwords > 0) A = wp[0];
+                    if (nwords > 1) B = wp[1];
+                    if (nwords > 2) C = wp[2];
+                    if (nwords > 3) D = wp[3];
+                    const bool hiw = sh >= 4;
+                    const uint32_t fs = (sh & 3) * 8;
+                    const uint32_t x0 = hiw ? A.y : A.x, x1 = hiw ? B.x : A.y, x2 = hiw ? B.y : B.x, x3 = hiw ? C.x : B.y,
+                                   x4 = hiw ? C.y : C.x, x5 = hiw ? D.x : C.y, x6 = hiw ? D.y : D.x;
+                    uint32_t o[6];
+                    o[0] = __funnelshift_r(x0, x1, fs); o[1] = __funnelshift_r(x1, x2, fs); o[2] = __funnelshift_r(x2, x3, fs);
+                    o[3] = __funnelshift_r(x3, x4, fs); o[4] = __funnelshift_r(x4, x5, fs); o[5] = __funnelshift_r(x5, x6, fs);
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if ((uint32_t)u < nw) md[u] = (uint8_t)(o[u >> 2] >> (8 * (u & 3)));
+                    if (mxw > 8) {
+#pragma unroll
+                        for (int u = 8; u < 16; u++)
+                            if ((uint32_t)u < nw) md[u] = (uint8_t)(o[u >> 2] >> (8 * (u & 3)));
+                    }
+                    if (mxw > 16) {
+#pragma unroll
+                        for (int u = 16; u < 24; u++)
+                            if ((uint32_t)u < nw) md[u] = (uint8_t)(o[u >> 2] >> (8 * (u & 3)));
+                    }
+                }
+                // Self-overlapping short matches with offset >= 8: 8 bytes at a time, all loads of a chunk before its
+                // stores (a chunk only reads bytes of earlier chunks).
+                const uint32_t nm = (go && !lng && !tiny && off < myML) ? myML : 0u;
                 const uint32_t mx = __reduce_max_sync(FULL, nm);
-                // one pair of running pointers and one remaining-byte count per lane: the accesses are
-                // base + immediate under a predicate (not a re-derived 64-bit address per byte)
                 const uint8_t* ps = msrc;
                 uint8_t* pd = md;
                 uint32_t rem = nm;

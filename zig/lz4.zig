@@ -44,7 +44,10 @@ const c = struct {
 
 // ---- lz4 namespace (reference src/lz4.zig) ----
 pub const lz4 = struct {
-    pub const Error = error{ OutputTooSmall, InputTooLarge, CorruptedData, DecompressionFailed, InvalidState, AllocationFailed };
+    /// The reference's six members (src/lz4.zig:48-55) plus two the reference cannot produce: `GpuUnavailable`
+    /// (status 200: no CUDA device / runtime failure — there is no CPU fallback) and `UnsupportedLevel` (status 201:
+    /// lz4hc levels 2 and 10..12, see lz4hc below).  Code that switches over lz4.Error needs an `else` arm for them.
+    pub const Error = error{ OutputTooSmall, InputTooLarge, CorruptedData, DecompressionFailed, InvalidState, AllocationFailed, GpuUnavailable, UnsupportedLevel };
     pub const MINMATCH = 4;
     pub const LZ4_MAX_INPUT_SIZE = 0x7E000000;
     pub const LZ4_DISTANCE_MAX = 65535;
@@ -57,7 +60,9 @@ pub const lz4 = struct {
             3 => error.CorruptedData,
             4 => error.DecompressionFailed,
             5 => error.InvalidState,
-            else => error.AllocationFailed, // 6, and 200+ (CUDA failure) have no closer member
+            6 => error.AllocationFailed,
+            201 => error.UnsupportedLevel,
+            else => error.GpuUnavailable, // 200 (B2LZ4_ERR_CUDA)
         };
     }
     pub fn compressBound(inputSize: usize) usize {
@@ -99,9 +104,15 @@ pub const lz4 = struct {
 // ---- lz4hc namespace (reference src/lz4hc.zig) ----
 pub const lz4hc = struct {
     pub const Error = lz4.Error;
+    /// The reference's level range (src/lz4hc.zig:28-31).  The accelerated path covers the hash-chain strategy,
+    /// levels 3..9 (and everything below 2, which the reference maps to 9); level 2 (LZ4MID) and 10..12 (optimal
+    /// parser) are other algorithms outside the hot-path scope: compressHC returns error.UnsupportedLevel for them
+    /// instead of silently compressing with a different level.
     pub const LZ4HC_CLEVEL_MIN = 2;
     pub const LZ4HC_CLEVEL_DEFAULT = 9;
     pub const LZ4HC_CLEVEL_MAX = 12;
+    pub const LZ4HC_CLEVEL_ACCELERATED_MIN = 3;
+    pub const LZ4HC_CLEVEL_ACCELERATED_MAX = 9;
     pub fn compressBound(inputSize: usize) usize {
         return c.b2lz4_compress_bound(inputSize);
     }
@@ -122,6 +133,20 @@ pub const lz4f = struct {
         HeaderChecksumInvalid,   ContentChecksumInvalid,    FrameDecodingAlreadyStarted,
         CompressionStateUninitialized, ParameterNull,       MaxCode,                  OutOfMemory,
     };
+    // size constants and isError, reference src/lz4f.zig:12-27,57-59
+    pub const MAGICNUMBER: u32 = 0x184D2204;
+    pub const MAGIC_SKIPPABLE_START: u32 = 0x184D2A50;
+    pub const MAGIC_SKIPPABLE_MASK: u32 = 0xFFFFFFF0;
+    pub const HEADER_SIZE_MIN: usize = 7;
+    pub const HEADER_SIZE_MAX: usize = 19;
+    pub const MIN_SIZE_TO_KNOW_HEADER_LENGTH: usize = 5;
+    pub const BLOCK_HEADER_SIZE: usize = 4;
+    pub const BLOCK_CHECKSUM_SIZE: usize = 4;
+    pub const CONTENT_CHECKSUM_SIZE: usize = 4;
+    pub const ENDMARK_SIZE: usize = 4;
+    pub fn isError(code: usize) bool {
+        return code > @as(usize, @bitCast(@as(isize, -65536)));
+    }
     pub const BlockSizeID = enum(u3) { default = 0, max64KB = 4, max256KB = 5, max1MB = 6, max4MB = 7 };
     pub const BlockMode = enum(u1) { linked = 0, independent = 1 };
     pub const ContentChecksum = enum(u1) { disabled = 0, enabled = 1 };
@@ -172,7 +197,8 @@ pub const lz4f = struct {
             error.CompressionStateUninitialized, error.ParameterNull,    error.MaxCode,                error.OutOfMemory,
         };
         if (status >= 100 and status < 100 + @as(c_int, members.len)) return members[@intCast(status - 100)];
-        return error.Generic;
+        if (status == 201) return error.CompressionLevelInvalid; // HC level 2 / 10..12: not on the accelerated path
+        return error.Generic; // 200: no CUDA device / runtime failure
     }
     pub fn compressFrameBound(srcSize: usize, prefs: ?Preferences) usize {
         const p = toC(prefs);
@@ -244,6 +270,7 @@ pub const Error = lz4.Error;
 pub const compressDefault = lz4.compressDefault;
 pub const compressFast = lz4.compressFast;
 pub const compressBound = lz4.compressBound;
+pub const compressDestSize = lz4.compressDestSize;
 pub const decompressSafe = lz4.decompressSafe;
 pub const decompressSafeUsingDict = lz4.decompressSafeUsingDict;
 pub const MINMATCH = lz4.MINMATCH;
