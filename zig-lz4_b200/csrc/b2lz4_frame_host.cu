@@ -541,6 +541,7 @@ int b2lz4f_compress_frame_mgpu(const void* src, size_t n, void* dst, size_t cap,
         B2_CUDA(cudaSetDevice(c->device));
         int rc = download(c, (uint8_t*)dst + j.out_off, c->stage_out[0].p, j.produced, c->stream); if (rc) return rc;
         B2_CUDA(cudaStreamSynchronize(c->stream));
+        B2_CUDA(c->mover.flush());
         return B2LZ4_OK;
     });
     { int rc = first_error(jobs); if (rc) return rc; }
@@ -607,6 +608,7 @@ int b2lz4f_decompress_frame_mgpu(const void* srcv, size_t n, void* dst, size_t c
         // every range but the last must fill its blocks exactly for the offsets to hold; the caller checks
         rc = download(c, (uint8_t*)dst + j.out_off, c->stage_out[0].p, j.produced, c->stream); if (rc) return rc;
         B2_CUDA(cudaStreamSynchronize(c->stream));
+        B2_CUDA(c->mover.flush());
         return B2LZ4_OK;
     });
     bool usual = first_error(jobs) == B2LZ4_OK;
@@ -665,6 +667,7 @@ static int emit_blocks(b2lz4f_cctx* cc, const uint8_t* h_a, size_t na, const uin
     rc = download(c, dst, c->stage_out[0].p, produced, s);
     if (rc) return rc;
     B2_CUDA(cudaStreamSynchronize(s));
+    B2_CUDA(c->mover.flush());
     *out = produced;
     return B2LZ4_OK;
 }

@@ -168,6 +168,7 @@ constexpr uint32_t PLAIN_SPAN = 18;
 constexpr uint32_t FAST_LEN_MAX = 1u << 24;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
@@ -439,8 +440,8 @@ __device__ __forceinline__ void token_deltas(uint32_t x, uint32_t xs, uint32_t k
     hi16 = (__byte_perm(d8, 0u, 0x4342) + __byte_perm(xm, 0u, 0x4342)) << 1;
 }
 
-__device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap,
-                                  const uint8_t* __restrict__ dict, uint32_t dict_len, bool has_dict, uint32_t lane,
+// (no dictionary here: the kernel sends dictionary decodes to the serial front end)
+__device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t lane,
                                   WarpStage* __restrict__ ws, uint32_t& olen, int& st) {
     uint32_t ip = 0, op = 0;
     st = ST_OK;
@@ -455,14 +456,11 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                 // ---------------- stage the next 256 (+32) stream bytes, 8-byte aligned ----------------
                 cb = (int32_t)ip - (int32_t)(reinterpret_cast<uintptr_t>(src + ip) & 7);
                 const uint2* g = reinterpret_cast<const uint2*>(src + cb);
-                uint2 w = make_uint2(0u, 0u);
+                uint2 w = make_uint2(0u, 0u), m = w;
                 if (cb + 8 * (int32_t)lane < (int32_t)n) w = __ldg(g + lane);   // a word that holds a stream byte is mapped
+                if (lane < CHUNK_MARGIN / 8 && cb + (int32_t)CHUNK + 8 * (int32_t)lane < (int32_t)n) m = __ldg(g + 32 + lane);
                 reinterpret_cast<uint2*>(ws->bytes)[lane] = w;
-                if (lane < CHUNK_MARGIN / 8) {
-                    uint2 m = make_uint2(0u, 0u);
-                    if (cb + (int32_t)CHUNK + 8 * (int32_t)lane < (int32_t)n) m = __ldg(g + 32 + lane);
-                    reinterpret_cast<uint2*>(ws->bytes)[32 + lane] = m;
-                }
+                if (lane < CHUNK_MARGIN / 8) reinterpret_cast<uint2*>(ws->bytes)[32 + lane] = m;
                 if (lane < 4 && ip + 1024 + lane * 128 < n) prefetch_l2(src + ip + 1024 + lane * 128);
                 __syncwarp();
                 const uint32_t nx = reinterpret_cast<const uint32_t*>(ws->bytes)[2 * lane + 2];   // the 4 bytes after mine
@@ -524,13 +522,15 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
             if (cut) k = (uint32_t)__ffs(bm) - 1;
             const uint32_t ipn = (uint32_t)(cb + (int32_t)(ws->pos[k] >> 1));
             if (lane >= k) { myLL = 0; myML = 0; }
+            // the next chunk's lines into L1 while this batch is expanded (its staging then costs an L1 hit, not an L2 round trip)
+            if (lane < 3 && ipn + lane * 128 < isafe) prefetch_l1(src + ipn + lane * 128);
             __syncwarp();                                            // staged bytes are dead from here (next chunk overwrites them)
             if (k != 0 && !expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
             ip = ipn;
             staged_ok = (int32_t)ip - cb <= (int32_t)CHUNK - 56;
             if (cut) {
                 // a long, broken or stream-ending token: one exact sequence, warp-wide, with the reference's checks
-                const uint4 r = exact_step_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
+                const uint4 r = exact_step_ool(src, n, dst, cap, nullptr, 0u, false, lane, ip, op);
                 ip = r.x; op = r.y;
                 if (r.w == 2) { st = (int)r.z; return; }
                 if (r.w == 1) { olen = op; return; }
@@ -539,7 +539,7 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
         }
     }
     // the exact tier finishes the block (or decides the error) from a state where all earlier sequences are complete
-    const uint2 r = finish_exact_ool(src, n, dst, cap, dict, dict_len, has_dict, lane, ip, op);
+    const uint2 r = finish_exact_ool(src, n, dst, cap, nullptr, 0u, false, lane, ip, op);
     olen = r.x;
     st = (int)r.y;
 }
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
             olen = r.x;
             st = (int)r.y;
         } else {
-            decode_block_fast(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, ws, olen, st);
+            decode_block_fast(src, n, dst, cap, lane, ws, olen, st);
         }
         if (lane == 0) {
             out_len[blk] = st == ST_OK ? olen : 0u;
