@@ -94,7 +94,7 @@ struct b2lz4_ctx {
     bool timing = false;
     float phase_ms[5] = {0, 0, 0, 0, 0};
     // workspace
-    b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, hc_work;
+    b2::DevBuf slots, csize, status, sums, rec_off, small, walk_off, walk_hdr, out_len, order, hc_work;
     b2::DevBuf idx_tiles, idx_pos, idx_jump;   // parallel frame index scratch
     b2::DevBuf dict_table;                     // primed hash table of the dictionary compressor
     b2::DevBuf ds_work;                        // compressDestSize: per-block search state + probe lengths/results

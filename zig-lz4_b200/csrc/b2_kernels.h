@@ -52,9 +52,11 @@ cudaError_t launch_dest_size_finish(const DestSizeState* state, uint32_t* consum
                                     uint32_t nblocks, cudaStream_t stream);
 
 // K2 — decompressor (k_decompress.cu).  hdr: optional frame block headers (bit31 = stored raw).
+// order_scratch (nblocks u32, optional) + block_size: frame blocks are decoded expensive-first (see k_order_heavy_first)
 cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint32_t* hdr, uint32_t* out_len,
                               int32_t* status, uint32_t nblocks, const uint8_t* dict, uint32_t dict_len,
-                              uint32_t* ticket, int num_sms, cudaStream_t stream);
+                              uint32_t* ticket, int num_sms, cudaStream_t stream, uint32_t* order_scratch = nullptr,
+                              uint32_t block_size = 0);
 // size-only parse (no output written): natural decoded size of each block, for foreign frames whose
 // non-final blocks are not exactly blockSize
 cudaError_t launch_decoded_size(const BlockSet& in, const uint32_t* hdr, uint32_t* out_len, int32_t* status,

@@ -72,7 +72,7 @@ int b2_hc_supported(int level) { return hc_nb_searches(level) >= 0 ? 1 : 0; }
 
 size_t b2lz4_ctx::workspace_bytes() const {
     size_t t = slots.cap + csize.cap + status.cap + sums.cap + rec_off.cap + small.cap + walk_off.cap + walk_hdr.cap +
-               out_len.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap + dict_table.cap + ds_work.cap;
+               out_len.cap + order.cap + hc_work.cap + stage_aux.cap + idx_tiles.cap + idx_pos.cap + idx_jump.cap + dict_table.cap + ds_work.cap;
     for (int i = 0; i < 3; i++) t += stage_in[i].cap + stage_out[i].cap;
     for (int i = 0; i < 2; i++) t += x_slots[i].cap + x_csize[i].cap + x_status[i].cap + x_sums[i].cap + x_rec_off[i].cap + x_small[i].cap;
     return t;
@@ -100,7 +100,10 @@ const char* b2lz4_status_name(int s) {
 }
 const char* b2lz4_last_cuda_error(void) { return g_cuda_err.c_str(); }
 uint64_t b2lz4_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-const char* b2lz4_version(void) { return "b2lz4 0.2 (sm_100a)"; }
+#ifndef B2_SRC_HASH
+#define B2_SRC_HASH "unknown"
+#endif
+const char* b2lz4_version(void) { return "b2lz4 0.2 (sm_100a) src:" B2_SRC_HASH; }
 int b2lz4_debug_tune(const char* key, int value) {
     if (!key) return -1;
     b2::Tune& t = b2::tune();
@@ -157,7 +160,7 @@ void b2lz4_ctx_destroy(b2lz4_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->slots, &c->csize, &c->status, &c->sums, &c->rec_off, &c->small, &c->walk_off, &c->walk_hdr,
-                      &c->out_len, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->dict_table, &c->ds_work, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
+                      &c->out_len, &c->order, &c->hc_work, &c->idx_tiles, &c->idx_pos, &c->idx_jump, &c->dict_table, &c->ds_work, &c->stage_in[0], &c->stage_in[1], &c->stage_in[2],
                       &c->stage_out[0], &c->stage_out[1], &c->stage_out[2], &c->stage_aux,
                       &c->x_slots[0], &c->x_slots[1], &c->x_csize[0], &c->x_csize[1], &c->x_status[0], &c->x_status[1],
                       &c->x_sums[0], &c->x_sums[1], &c->x_rec_off[0], &c->x_rec_off[1], &c->x_small[0], &c->x_small[1]};
@@ -470,8 +473,9 @@ static int decode_blocks_dev(b2lz4_ctx* c, const uint8_t* src, uint64_t n, const
     T.mark(2);
     BlockSet in = explicit_in(src, d_off, d_hdr, 0x7FFFFFFFu);
     OutSet out = regular_out(dst, bs, cap, bs);
+    B2_CUDA(c->order.ensure((size_t)nb * 4 + 4));
     if (nb) B2_CUDA(launch_decompress(in, out, d_hdr, c->out_len.as<uint32_t>(), c->status.as<int32_t>(), nb, nullptr, 0,
-                                      c->d_ticket(), c->num_sms, s));
+                                      c->d_ticket(), c->num_sms, s, c->order.as<uint32_t>(), bs));
     T.mark(3);
     B2_CUDA(launch_decode_summary(c->out_len.as<uint32_t>(), c->status.as<int32_t>(), c->sums.as<uint32_t>(), src, d_off, d_hdr,
                                   nb, bs, bc ? 1 : 0, c->d_summary(), s));

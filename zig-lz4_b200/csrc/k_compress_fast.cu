@@ -358,13 +358,13 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
             const uint32_t need = (!lit_in_lanes && t < 0) ? 1u : 0u;   // literals not in the window's registers (chained window)
             const uint8_t* lp = src + anchor + (lane ? lane - 1 : 0);
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u8 %0, [%2];\n\t}"
-                : "+r"(bv) : "r"(need), "l"(__cvta_generic_to_global(lp)));
+                : "+r"(bv) : "r"(need), "l"(reinterpret_cast<uint64_t>(lp)));   // src is global memory (asserted by the kernel): its generic address IS its global address
         }
         const uint32_t ob = t == 0 ? offset : offset >> 8;
         bv = t >= 0 ? ob : bv;
         bv = lane == 0 ? ((LL << 4) | ml) : bv;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %0, 2;\n\t@p st.global.u8 [%1], %2;\n\t}"
-                     :: "r"(t), "l"(__cvta_generic_to_global(dst + op + lane)), "r"(bv) : "memory");
+                     :: "r"(t), "l"(reinterpret_cast<uint64_t>(dst + op + lane)), "r"(bv) : "memory");
         op = seq_end;
     } else {
         // the caller computes the size itself, so that `op` never depends on a call result
@@ -563,11 +563,19 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 const uint32_t L = (uint32_t)__ffs(m) - 1;
                 V |= lane_range(lo + 1, L);
                 const uint32_t mpos = base + L;
-                const uint32_t mcand = __shfl_sync(FULL, pv ? base + (uint32_t)pl : old, L);
+                // blocks <= 64 KiB (u16 table): candidate position and its pre-measured extension travel in one shuffle
+                uint32_t mcand, pk;
+                if (sizeof(TableT) == 2) {
+                    const uint32_t both = __shfl_sync(FULL, (pv ? base + (uint32_t)pl : old) | (mlpk << 16), L);
+                    mcand = both & 0xFFFFu;
+                    pk = both >> 16;
+                } else {
+                    mcand = __shfl_sync(FULL, pv ? base + (uint32_t)pl : old, L);
+                    pk = __shfl_sync(FULL, mlpk, L);
+                }
                 const uint32_t LL = mpos - anchor;                       // anchor == base + lo, except in a chained window's first search
                 uint32_t ml;
                 if (mcand < base) {                                      // table candidate: extension already measured
-                    const uint32_t pk = __shfl_sync(FULL, mlpk, L);
                     ml = pk & 0xFFu;
                     if (pk >> 8) ml += extend_bytes(src, mpos + MINMATCH + ml, mcand + MINMATCH + ml, mlimit, lane);
                 } else {                                                 // candidate inside the window (runs, short periods)

@@ -548,7 +548,8 @@ template <int MIN_CTAS, int VARIANT>
 __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in, OutSet out, const uint32_t* __restrict__ hdr,
                                                            uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
                                                            uint32_t nblocks, const uint8_t* __restrict__ dict,
-                                                           uint32_t dict_len, int has_dict, uint32_t* ticket) {
+                                                           uint32_t dict_len, int has_dict, uint32_t* ticket,
+                                                           const uint32_t* __restrict__ order) {
     __shared__ WarpStage stage[VARIANT == 1 ? 1 : K2_WARPS];
     const uint32_t lane = lane_id();
     WarpStage* ws = &stage[VARIANT == 1 ? 0 : (threadIdx.x >> 5)];
@@ -561,6 +562,7 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
         if (lane == 0) blk = atomicAdd(ticket, 1u);
         blk = __shfl_sync(FULL, blk, 0);
         if (blk >= nblocks) break;
+        if (order) blk = order[blk];             // expensive blocks first (k_order_heavy_first): the kernel's tail is cheap blocks
         const uint8_t* src; uint32_t n;
         uint8_t* dst; uint32_t cap;
         in.get(blk, src, n);
@@ -597,6 +599,44 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
     }
 }
 
+// Stable partition of the block indices: blocks whose stream is at least 1/6 of the block size first (text, binary:
+// ~1.4 ms of a warp each), stored and highly compressible blocks after them.  One block takes a third of the whole
+// kernel's duration on the bench workload, so with index order the kernel ends on a tail of expensive blocks.
+__global__ void __launch_bounds__(1024) k_order_heavy_first(const uint32_t* __restrict__ hdr, uint32_t nblocks, uint32_t block_size,
+                                                            uint32_t* __restrict__ order) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t total_h;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto heavy = [&](uint32_t i) { const uint32_t h = hdr[i]; return !(h & 0x80000000u) && (uint64_t)(h & 0x7FFFFFFFu) * 6 >= block_size; };
+    uint32_t cnt = 0;
+    for (uint32_t i = tid; i < nblocks; i += 1024) cnt += heavy(i) ? 1u : 0u;
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t t = __reduce_add_sync(FULL, wsum[lane]);
+        if (lane == 0) total_h = t;
+    }
+    __syncthreads();
+    uint32_t run_h = 0, run_l = total_h;
+    for (uint32_t t0 = 0; t0 < nblocks; t0 += 1024) {
+        const uint32_t i = t0 + tid;
+        const bool in = i < nblocks, h = in && heavy(i);
+        const uint32_t bm = __ballot_sync(FULL, h);
+        __syncthreads();
+        if (lane == 0) wsum[warp] = (uint32_t)__popc(bm);
+        __syncthreads();
+        uint32_t before = 0, tile_h = 0;
+        for (uint32_t w = 0; w < 32; w++) { const uint32_t v = wsum[w]; if (w < warp) before += v; tile_h += v; }
+        const uint32_t rank_h = before + (uint32_t)__popc(bm & lanemask_lt());
+        const uint32_t valid = nblocks - t0 < 1024 ? nblocks - t0 : 1024;
+        if (h) order[run_h + rank_h] = i;
+        else if (in) order[run_l + (tid - rank_h)] = i;
+        run_h += tile_h;
+        run_l += valid - tile_h;
+    }
+}
+
 // Natural decoded size of every block (unbounded output, nothing written).
 __global__ void __launch_bounds__(K2_THREADS) k_decoded_size(BlockSet in, const uint32_t* __restrict__ hdr,
                                                              uint32_t* __restrict__ out_len,
@@ -616,10 +656,16 @@ __global__ void __launch_bounds__(K2_THREADS) k_decoded_size(BlockSet in, const 
 
 cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint32_t* hdr, uint32_t* out_len,
                               int32_t* status, uint32_t nblocks, const uint8_t* dict, uint32_t dict_len,
-                              uint32_t* ticket, int num_sms, cudaStream_t stream) {
+                              uint32_t* ticket, int num_sms, cudaStream_t stream, uint32_t* order_scratch, uint32_t block_size) {
     if (nblocks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    const uint32_t* order = nullptr;
+    if (order_scratch && hdr && block_size && nblocks > (uint32_t)num_sms * 8 && tune().spare[0] == 0) {
+        k_order_heavy_first<<<1, 1024, 0, stream>>>(hdr, nblocks, block_size, order_scratch);
+        count_launch();
+        order = order_scratch;
+    }
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
     // CTAs of 4 warps per SM: 8 (64 registers, no spills) by default; b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
     // occupancy experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end (10 per SM).
@@ -628,7 +674,7 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
-                                                                              dict_len, dict != nullptr ? 1 : 0, ticket)
+                                                                              dict_len, dict != nullptr ? 1 : 0, ticket, order)
     if (variant == 1) {
         if (occ == 12) B2_K2_LAUNCH(12, 1); else if (occ == 8) B2_K2_LAUNCH(8, 1); else B2_K2_LAUNCH(10, 1);
     } else {
