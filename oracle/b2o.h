@@ -14,9 +14,14 @@
  *   - stock-decoder acceptance (liblz4.so.1 LZ4_decompress_safe / LZ4F_decompress, pyarrow) in
  *     place of the `lz4` CLI the reference shells out to (src/test_compat.zig:141-254),
  *   - XXH32 against libxxhash.so.0 / python-xxhash (Zig std.hash.XxHash32 is standard XXH32),
- *   - the second-source vectors of SURVEY.md §8(c) (an independent Python restatement).
- * Compressed-byte parity with the *Zig binary* is therefore pinned by the algorithm text only:
- * "parity unpinned" against reference-binary output, and DESIGN.md says so.
+ *   - the second-source vectors of SURVEY.md §8(c) (an independent Python restatement, fast path),
+ *   - tests/second_source/zlz4_second.py: a second restatement of the WHOLE path (fast, decoder, HC 3..9, frames,
+ *     XXH32) written independently from the .zig text, whose committed outputs (tests/golden/
+ *     second_source_vectors.json: 324 blocks, 208 frames, 49 decoder exits) this oracle must reproduce
+ *     (tests/test_second_source.py).
+ * There is still neither a reference binary nor a reference-held vector: "parity unpinned" against
+ * reference-binary output in that strict sense, pinned by two independent derivations agreeing, and DESIGN.md §2
+ * says so.
  *
  * Status codes (shared numbering with include/b2lz4.h, but deliberately re-declared here so the
  * oracle stays independent of the product headers):
