@@ -45,11 +45,25 @@ struct HcWork {
     uint32_t pad[15];
 };
 
-// one HcWork (256 KiB of tables) per warp that a launch over `nblocks` blocks can have in flight — not per resident
-// warp of the device: a single small block needs 1 MiB, not 2.5 GB
+// Jump variant (round 2): next to the reference's chainTable (jump[0]: distance to the previous position of the same
+// bucket) the distances to the 2nd, 4th, 8th and 16th predecessor, filled in when a position is inserted (each level is
+// one read of the previous level at the predecessor).  A search then reaches its 32 next candidates with at most five
+// dependent reads per lane (lane j follows the bits of j) instead of 32 dependent reads of one chain: the walk is what
+// K3 spends its time on (every hop a DRAM round trip, issue slots 6 % busy).  Same candidates, same order, same bytes.
+constexpr int HC_LEVELS = 5;
+struct HcWorkJ {
+    uint32_t hash[HC_HASH];
+    uint16_t jump[HC_LEVELS][HC_CHAIN];
+    uint32_t base;
+    uint32_t pad[15];
+};
+static bool hc_jump() { return tune().k3_variant != 16; }     // 16 = the round-1 single-chain walk, for A/B runs
+
+// one work area per warp that a launch over `nblocks` blocks can have in flight — not per resident warp of the device:
+// a single small block needs a few MiB, not gigabytes
 size_t hc_work_bytes(int num_sms, uint32_t nblocks) {
     const size_t ctas = (nblocks + HC_WARPS - 1) / HC_WARPS, max_ctas = (size_t)num_sms * HC_CTAS_PER_SM;
-    return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * sizeof(HcWork);
+    return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * (sizeof(HcWorkJ) > sizeof(HcWork) ? sizeof(HcWorkJ) : sizeof(HcWork));
 }
 
 __device__ __forceinline__ uint32_t hashHC(uint32_t v) { return (v * HASH_MULTIPLIER) >> 17; }  // :129-131
@@ -107,8 +121,11 @@ __device__ __forceinline__ uint32_t lane_count(const uint8_t* __restrict__ src, 
     return c;
 }
 
+template <bool JUMP>
 __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
-                                  HcWork* w, int nbs, uint32_t lane, uint32_t& olen, int& st) {
+                                  void* wv, int nbs, uint32_t lane, uint32_t& olen, int& st) {
+    HcWork* w = reinterpret_cast<HcWork*>(wv);                 // hash[] first and `base` are read through the variant's type
+    HcWorkJ* wj = reinterpret_cast<HcWorkJ*>(wv);
     st = ST_OK;
     olen = 0;
     if (n == 0) return;                                                  // :1443
@@ -123,7 +140,8 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
         return;
     }
     // epoch base for this block's bucket values
-    uint32_t base = w->base;
+    uint32_t* basep = JUMP ? &wj->base : &w->base;
+    uint32_t base = *basep;
     if (base > 0xFFFFFFFFu - n - 16u) {   // would wrap: re-zero once
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4* t4 = reinterpret_cast<uint4*>(w->hash);
@@ -131,9 +149,9 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
         base = 0;
     }
     __syncwarp();
-    if (lane == 0) w->base = base + n;
+    if (lane == 0) *basep = base + n;
     uint32_t* H = w->hash;
-    uint16_t* C = w->chain;
+    uint16_t* C = JUMP ? wj->jump[0] : w->chain;
     const bool patternAnalysis = nbs > 128;                              // :983
     const uint32_t mflimit = n - MFLIMIT, mlimit = n - LASTLITERALS;
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
@@ -161,6 +179,25 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                 if ((peers & gt) == 0) H[h] = base + idx;
             }
             __syncwarp();
+            if (JUMP) {
+                // distance to the 2nd, 4th, 8th, 16th predecessor: level k = level k-1 here + level k-1 at that predecessor
+                // (already complete: an earlier position, or a lane of this batch that wrote it one step ago); 65535 =
+                // "out of reach", as in the reference's clamp (:505)
+                uint32_t dk = delta;
+#pragma unroll
+                for (int k = 1; k < HC_LEVELS; k++) {
+                    uint32_t nd = MAX_DISTANCE;
+                    if (act) {
+                        if (dk < MAX_DISTANCE && dk <= idx) {
+                            const uint32_t sum = dk + wj->jump[k - 1][(idx - dk) & (HC_CHAIN - 1)];
+                            nd = sum > MAX_DISTANCE ? MAX_DISTANCE : sum;
+                        }
+                        wj->jump[k][idx & (HC_CHAIN - 1)] = (uint16_t)nd;
+                    }
+                    __syncwarp();
+                    dk = nd;
+                }
+            }
             ntu += 32;
         }
         ntu = ip;
@@ -171,8 +208,58 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
         uint32_t m;
         { uint32_t v = H[hashHC(pattern)]; m = v >= base ? v - base : 0; }   // :563
         if (m != 0) {                                                        // :566
-            int attempts = nbs;
             uint32_t final_m = m;
+            if (JUMP) {
+                // chain positions P_0 = m, P_{i+1} = P_i - chain[P_i] (:619-621), 32 per round: lane j jumps from the
+                // round's first position by the bits of j.  A position is visited while it is > 0 (:571), within
+                // 65535 of ip (:573) and attempts are left; positions only decrease, so the visited lanes are a prefix.
+                uint32_t basepos = m;
+                for (uint32_t round = 0;; round++) {
+                    uint32_t pos = basepos;
+                    bool ok = true;
+#pragma unroll
+                    for (int k = HC_LEVELS - 1; k >= 0; k--) {
+                        if ((lane >> k) & 1) {
+                            const uint32_t d = ok ? (uint32_t)wj->jump[k][pos & (HC_CHAIN - 1)] : 0u;
+                            if (d == 0 || d > pos) ok = false; else pos -= d;
+                        }
+                    }
+                    const bool visit = ok && pos > 0 && pos <= ip && ip - pos <= MAX_DISTANCE && round * 32 + lane < (uint32_t)nbs;
+                    const uint32_t vm = __ballot_sync(FULL, visit);
+                    uint32_t cnt = vm == FULL ? 32u : (uint32_t)__ffs(~vm) - 1;
+                    // the hop after each visited position: next round's start, or where the walk stops
+                    uint32_t nxt = pos;
+                    bool stuck = false;                                                          // :620 delta == 0 or delta > matchIndex
+                    if (lane < cnt) {
+                        const uint32_t d0 = C[pos & (HC_CHAIN - 1)];
+                        stuck = d0 == 0 || d0 > pos;
+                        if (!stuck) nxt = pos - d0;
+                    }
+                    const uint32_t sm = __ballot_sync(FULL, stuck);
+                    if (sm) cnt = (uint32_t)__ffs(sm);                                           // that position is still a candidate
+                    const uint32_t my_cand = pos;
+                    uint32_t len = 0;
+                    if (lane < cnt && ldg_u32(src + my_cand) == pattern)                         // :586
+                        len = MINMATCH + lane_count(src, ip + MINMATCH, my_cand + MINMATCH, mlimit);
+                    const uint32_t xm = __ballot_sync(FULL, len > (uint32_t)nbs);               // :613
+                    const uint32_t X = xm ? (uint32_t)__ffs(xm) - 1 : 32;
+                    const uint32_t l = (lane < cnt && lane <= X) ? len : 0;
+                    const uint32_t mx = __reduce_max_sync(FULL, l);
+                    if (mx > best_len) {                                                         // :607
+                        const uint32_t who = (uint32_t)__ffs(__ballot_sync(FULL, l == mx)) - 1;
+                        best_len = mx;
+                        best_off = ip - __shfl_sync(FULL, my_cand, who);
+                    }
+                    if (xm) { final_m = __shfl_sync(FULL, my_cand, X); break; }
+                    if (sm) { final_m = __shfl_sync(FULL, my_cand, cnt - 1); break; }
+                    if (cnt < 32 || (round + 1) * 32 >= (uint32_t)nbs) {
+                        final_m = cnt == 0 ? basepos : __shfl_sync(FULL, nxt, cnt - 1);
+                        break;
+                    }
+                    basepos = __shfl_sync(FULL, nxt, 31);
+                }
+            } else {
+            int attempts = nbs;
             bool done = false;
             while (!done) {
                 uint32_t my_cand = 0, cnt = 0;
@@ -199,6 +286,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     best_off = ip - __shfl_sync(FULL, my_cand, who);
                 }
                 if (xm) { done = true; final_m = __shfl_sync(FULL, my_cand, X); }
+            }
             }
             if (patternAnalysis) {                                                               // :626
                 uint32_t delta = C[final_m & (HC_CHAIN - 1)];
@@ -263,13 +351,13 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     olen = op;
 }
 
-template <int CTAS>
+template <int CTAS, bool JUMP>
 __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                                int32_t* __restrict__ status, uint32_t nblocks, int nbs,
-                                                               HcWork* work, uint32_t* ticket) {
+                                                               uint8_t* work, uint32_t* ticket) {
     const uint32_t lane = lane_id();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    HcWork* w = work + gw;
+    void* w = work + (size_t)gw * (JUMP ? sizeof(HcWorkJ) : sizeof(HcWork));
     for (;;) {
         uint32_t blk = 0;
         if (lane == 0) blk = atomicAdd(ticket, 1u);
@@ -280,7 +368,7 @@ __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in
         in.get(blk, src, n);
         out.get(blk, dst, cap);
         uint32_t olen; int st;
-        compress_block_hc(src, n, dst, cap, w, nbs, lane, olen, st);
+        compress_block_hc<JUMP>(src, n, dst, cap, w, nbs, lane, olen, st);
         if (lane == 0) { out_len[blk] = st == ST_OK ? olen : 0u; status[blk] = st; }
         __syncwarp();
     }
@@ -292,23 +380,20 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     const uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
-    uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
-    const int cap_ctas = tune().k3_variant;                 // experiment: at most this many CTAs (of 4 warps) per SM
+    const uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
+    const int cap_ctas = tune().k3_variant;                 // experiment: 1..8 = at most this many CTAs (of 4 warps) per SM
+    const bool jump = hc_jump();
+#define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket)
     if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
         const uint32_t g = (uint32_t)(num_sms * cap_ctas);
-        k_compress_hc<HC_CTAS_PER_SM_FEW><<<want < g ? want : g, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
-                                                                                 reinterpret_cast<HcWork*>(work), ticket);
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (want <= few) {
-        k_compress_hc<HC_CTAS_PER_SM_FEW><<<want, HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches,
-                                                                              reinterpret_cast<HcWork*>(work), ticket);
+        B2_K3(HC_CTAS_PER_SM_FEW, true, want < g ? want : g);
+    } else if (want <= few) {
+        if (jump) B2_K3(HC_CTAS_PER_SM_FEW, true, want); else B2_K3(HC_CTAS_PER_SM_FEW, false, want);
     } else {
         const uint32_t maxg = (uint32_t)(num_sms * HC_CTAS_PER_SM);
-        k_compress_hc<HC_CTAS_PER_SM><<<want < maxg ? want : maxg, HC_WARPS * 32, 0, stream>>>(
-            in, out, out_len, status, nblocks, nb_searches, reinterpret_cast<HcWork*>(work), ticket);
+        if (jump) B2_K3(HC_CTAS_PER_SM, true, want < maxg ? want : maxg); else B2_K3(HC_CTAS_PER_SM, false, want < maxg ? want : maxg);
     }
+#undef B2_K3
     count_launch();
     return cudaGetLastError();
 }
