@@ -121,9 +121,36 @@ __device__ __forceinline__ uint32_t lane_count(const uint8_t* __restrict__ src, 
     return c;
 }
 
+// One candidate of the chain, one lane: 4-byte check (:586) + lz4Count (:587-591), with ONE 16-byte read at the candidate
+// serving the check and the first 5..12 bytes of the count (the candidate is a random position of the block: every read
+// of it is a DRAM or L2 round trip, and the 4-bytes-at-a-time count made 3-5 of them per candidate).  f1..f3: the
+// 12 bytes after ip + 4 (the same for every candidate of a search).  Returns 0 or the match length.
+__device__ __forceinline__ uint32_t eval_candidate(const uint8_t* __restrict__ src, uint32_t ip, uint32_t cand, uint32_t pattern,
+                                                   uint32_t f1, uint32_t f2, uint32_t f3, uint32_t mlimit) {
+    const uintptr_t ca = reinterpret_cast<uintptr_t>(src + cand);
+    const uint2* c8 = reinterpret_cast<const uint2*>(ca & ~uintptr_t(7));
+    const uint2 A = __ldg(c8), B = __ldg(c8 + 1);     // the second word holds src[cand + 8 - c]: inside the block (cand <= n - 13)
+    const uint32_t c = (uint32_t)(ca & 7), sh = (c & 3) * 8;
+    const bool hiw = c >= 4;
+    const uint32_t w0 = hiw ? A.y : A.x, w1 = hiw ? B.x : A.y, w2 = hiw ? B.y : B.x, w3 = hiw ? 0u : B.y;
+    if (__funnelshift_r(w0, w1, sh) != pattern) return 0;
+    const uint32_t m1 = __funnelshift_r(w1, w2, sh), m2 = __funnelshift_r(w2, w3, sh), m3 = __funnelshift_r(w3, 0u, sh);
+    const uint32_t room = mlimit - (ip + MINMATCH);                   // bytes the count may still take on the ip side (>= 3)
+    uint32_t avail = 12 - c;                                          // candidate bytes staged after the first four
+    if (avail > room) avail = room;
+    const uint32_t x1 = f1 ^ m1, x2 = f2 ^ m2, x3 = f3 ^ m3;
+    const uint32_t c1 = (uint32_t)__clz(__brev(x1)) >> 3, c2 = (uint32_t)__clz(__brev(x2)) >> 3, c3 = (uint32_t)__clz(__brev(x3)) >> 3;
+    const uint32_t d = c1 + (c1 == 4 ? c2 + (c2 == 4 ? c3 : 0u) : 0u);
+    if (d < avail) return MINMATCH + d;
+    if (avail == room) return MINMATCH + room;
+    return MINMATCH + avail + lane_count(src, ip + MINMATCH + avail, cand + MINMATCH + avail, mlimit);
+}
+
+// JUMP: the block may switch to jump mode (jump tables maintained and used) once its chains prove long: the tables cost
+// four more dependent reads per inserted batch, which short chains (binary records, low levels) never earn back.
 template <bool JUMP>
 __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
-                                  void* wv, int nbs, uint32_t lane, uint32_t& olen, int& st) {
+                                  void* wv, int nbs, uint32_t jump_after, uint32_t lane, uint32_t& olen, int& st) {
     HcWork* w = reinterpret_cast<HcWork*>(wv);                 // hash[] first and `base` are read through the variant's type
     HcWorkJ* wj = reinterpret_cast<HcWorkJ*>(wv);
     st = ST_OK;
@@ -156,6 +183,8 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     const uint32_t mflimit = n - MFLIMIT, mlimit = n - LASTLITERALS;
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
     uint32_t ip = 0, ntu = 0;
+    bool jm = false;                       // jump mode on
+    uint32_t nsearch = 0, nhops = 0;       // chain statistics while it is off
 
     while (ip <= mflimit) {                                              // :1009
         // ---------------- insertHC(ctx, ip): positions [ntu, ip), :491-510 ----------------
@@ -179,7 +208,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                 if ((peers & gt) == 0) H[h] = base + idx;
             }
             __syncwarp();
-            if (JUMP) {
+            if (JUMP && jm) {
                 // distance to the 2nd, 4th, 8th, 16th predecessor: level k = level k-1 here + level k-1 at that predecessor
                 // (already complete: an earlier position, or a lane of this batch that wrote it one step ago); 65535 =
                 // "out of reach", as in the reference's clamp (:505)
@@ -204,12 +233,15 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
 
         // ---------------- insertAndGetWiderMatch, :538-681 ----------------
         const uint32_t pattern = ldg_u32(src + ip);
+        // the 12 bytes after ip + 4 (ip + 16 <= n + 4: the last word may reach past the block by up to 4 bytes only when
+        // ip is within 4 of n - 12; those bytes are never counted — eval_candidate clips at mlimit — but must be readable)
+        const uint32_t f1 = ldg_u32(src + ip + 4), f2 = ip + 12 <= n ? ldg_u32(src + ip + 8) : 0u, f3 = ip + 16 <= n ? ldg_u32(src + ip + 12) : 0u;
         uint32_t best_len = MINMATCH - 1, best_off = 0;
         uint32_t m;
         { uint32_t v = H[hashHC(pattern)]; m = v >= base ? v - base : 0; }   // :563
         if (m != 0) {                                                        // :566
             uint32_t final_m = m;
-            if (JUMP) {
+            if (JUMP && jm) {
                 // chain positions P_0 = m, P_{i+1} = P_i - chain[P_i] (:619-621), 32 per round: lane j jumps from the
                 // round's first position by the bits of j.  A position is visited while it is > 0 (:571), within
                 // 65535 of ip (:573) and attempts are left; positions only decrease, so the visited lanes are a prefix.
@@ -239,8 +271,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     if (sm) cnt = (uint32_t)__ffs(sm);                                           // that position is still a candidate
                     const uint32_t my_cand = pos;
                     uint32_t len = 0;
-                    if (lane < cnt && ldg_u32(src + my_cand) == pattern)                         // :586
-                        len = MINMATCH + lane_count(src, ip + MINMATCH, my_cand + MINMATCH, mlimit);
+                    if (lane < cnt) len = eval_candidate(src, ip, my_cand, pattern, f1, f2, f3, mlimit);   // :586-591
                     const uint32_t xm = __ballot_sync(FULL, len > (uint32_t)nbs);               // :613
                     const uint32_t X = xm ? (uint32_t)__ffs(xm) - 1 : 32;
                     const uint32_t l = (lane < cnt && lane <= X) ? len : 0;
@@ -274,8 +305,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     m -= delta;
                 }
                 uint32_t len = 0;
-                if (lane < cnt && ldg_u32(src + my_cand) == pattern)                             // :586
-                    len = MINMATCH + lane_count(src, ip + MINMATCH, my_cand + MINMATCH, mlimit);
+                if (lane < cnt) len = eval_candidate(src, ip, my_cand, pattern, f1, f2, f3, mlimit);           // :586-591
                 uint32_t xm = __ballot_sync(FULL, len > (uint32_t)nbs);                          // :613
                 uint32_t X = xm ? (uint32_t)__ffs(xm) - 1 : 32;
                 uint32_t l = (lane < cnt && lane <= X) ? len : 0;
@@ -286,6 +316,35 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     best_off = ip - __shfl_sync(FULL, my_cand, who);
                 }
                 if (xm) { done = true; final_m = __shfl_sync(FULL, my_cand, X); }
+            }
+            if (JUMP) {
+                nsearch++;
+                nhops += (uint32_t)(nbs - attempts);
+                if (nsearch >= 64 && nhops > jump_after * nsearch) {
+                    // long chains: build the jump levels of every position a later search can still reach, oldest first
+                    // (a level reads the level below at a predecessor; predecessors below `lo` are out of every later
+                    // search's reach, whatever their stale entries say, and so is everything reached through them)
+                    const uint32_t lo = ip > MAX_DISTANCE ? ip - MAX_DISTANCE : 0;
+                    for (uint32_t b0 = lo; b0 < ip; b0 += 32) {
+                        const uint32_t idx = b0 + lane;
+                        const bool act = idx < ip;
+                        uint32_t dk = act ? (uint32_t)C[idx & (HC_CHAIN - 1)] : MAX_DISTANCE;
+#pragma unroll
+                        for (int k = 1; k < HC_LEVELS; k++) {
+                            uint32_t nd = MAX_DISTANCE;
+                            if (act) {
+                                if (dk < MAX_DISTANCE && dk <= idx) {
+                                    const uint32_t sum = dk + wj->jump[k - 1][(idx - dk) & (HC_CHAIN - 1)];
+                                    nd = sum > MAX_DISTANCE ? MAX_DISTANCE : sum;
+                                }
+                                wj->jump[k][idx & (HC_CHAIN - 1)] = (uint16_t)nd;
+                            }
+                            __syncwarp();
+                            dk = nd;
+                        }
+                    }
+                    jm = true;
+                }
             }
             }
             if (patternAnalysis) {                                                               // :626
@@ -354,7 +413,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
 template <int CTAS, bool JUMP>
 __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                                int32_t* __restrict__ status, uint32_t nblocks, int nbs,
-                                                               uint8_t* work, uint32_t* ticket) {
+                                                               uint8_t* work, uint32_t* ticket, uint32_t jump_after) {
     const uint32_t lane = lane_id();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     void* w = work + (size_t)gw * (JUMP ? sizeof(HcWorkJ) : sizeof(HcWork));
@@ -368,7 +427,7 @@ __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in
         in.get(blk, src, n);
         out.get(blk, dst, cap);
         uint32_t olen; int st;
-        compress_block_hc<JUMP>(src, n, dst, cap, w, nbs, lane, olen, st);
+        compress_block_hc<JUMP>(src, n, dst, cap, w, nbs, jump_after, lane, olen, st);
         if (lane == 0) { out_len[blk] = st == ST_OK ? olen : 0u; status[blk] = st; }
         __syncwarp();
     }
@@ -382,8 +441,10 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     const uint32_t want = (nblocks + HC_WARPS - 1) / HC_WARPS;
     const uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
     const int cap_ctas = tune().k3_variant;                 // experiment: 1..8 = at most this many CTAs (of 4 warps) per SM
-    const bool jump = hc_jump();
-#define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket)
+    const bool jump = hc_jump() && nb_searches > 32;         // chains of at most 32 hops never earn the tables back
+    // a block switches to jump mode when its searches average more than this many chain hops (spare1 overrides: experiments)
+    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 24u;
+#define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket, jump_after)
     if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
         const uint32_t g = (uint32_t)(num_sms * cap_ctas);
         B2_K3(HC_CTAS_PER_SM_FEW, true, want < g ? want : g);
