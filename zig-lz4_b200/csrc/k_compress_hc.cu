@@ -184,7 +184,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
     uint32_t ip = 0, ntu = 0;
     bool jm = false;                       // jump mode on
-    uint32_t nsearch = 0, nhops = 0;       // chain statistics while it is off
+    uint32_t nsearch = 0, nhops = 0, dsum = 0;   // chain statistics while it is off: searches, hops, sum of hop distances / 256
 
     while (ip <= mflimit) {                                              // :1009
         // ---------------- insertHC(ctx, ip): positions [ntu, ip), :491-510 ----------------
@@ -303,6 +303,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     uint32_t delta = C[m & (HC_CHAIN - 1)];                                      // :619
                     if (delta == 0 || delta > m) { done = true; final_m = m; break; }
                     m -= delta;
+                    if (JUMP) dsum += delta >> 8;
                 }
                 uint32_t len = 0;
                 if (lane < cnt) len = eval_candidate(src, ip, my_cand, pattern, f1, f2, f3, mlimit);           // :586-591
@@ -320,7 +321,9 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
             if (JUMP) {
                 nsearch++;
                 nhops += (uint32_t)(nbs - attempts);
-                if (nsearch >= 64 && nhops > jump_after * nsearch) {
+                // long chains whose hops land far apart (each one a DRAM round trip): text.  Chains of near neighbours
+                // (records with a repeated field: hops of a few dozen positions, served by L1/L2) are faster walked as they are.
+                if (nsearch >= 64 && nhops > jump_after * nsearch && dsum > 2 * nhops) {
                     // long chains: build the jump levels of every position a later search can still reach, oldest first
                     // (a level reads the level below at a predecessor; predecessors below `lo` are out of every later
                     // search's reach, whatever their stale entries say, and so is everything reached through them)
