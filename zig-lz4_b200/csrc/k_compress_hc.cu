@@ -38,12 +38,6 @@ constexpr int HC_CTAS_PER_SM = 16;          // workspace is sized for the 64-war
 constexpr int HC_CTAS_PER_SM_FEW = 8;       // 32 warps per SM, 56 registers, no spills
 constexpr uint32_t HC_HASH = 32768, HC_CHAIN = 65536;
 
-struct HcWork {
-    uint32_t hash[HC_HASH];
-    uint16_t chain[HC_CHAIN];
-    uint32_t base;          // epoch base of the bucket values (persists across launches)
-    uint32_t pad[15];
-};
 
 // Jump variant (round 2): next to the reference's chainTable (jump[0]: distance to the previous position of the same
 // bucket) the distances to the 2nd, 4th, 8th and 16th predecessor, filled in when a position is inserted (each level is
@@ -51,10 +45,12 @@ struct HcWork {
 // dependent reads per lane (lane j follows the bits of j) instead of 32 dependent reads of one chain: the walk is what
 // K3 spends its time on (every hop a DRAM round trip, issue slots 6 % busy).  Same candidates, same order, same bytes.
 constexpr int HC_LEVELS = 5;
-struct HcWorkJ {
+// ONE layout for every kernel variant: the epoch base and the bucket values of a work area must mean the same thing to
+// whichever variant runs next on it (a variant that kept `base` elsewhere would read table bytes as its epoch).
+struct HcWork {
     uint32_t hash[HC_HASH];
-    uint16_t jump[HC_LEVELS][HC_CHAIN];
-    uint32_t base;
+    uint16_t jump[HC_LEVELS][HC_CHAIN];   // jump[0] is the reference's chainTable
+    uint32_t base;                        // epoch base of the bucket values (persists across launches)
     uint32_t pad[15];
 };
 static bool hc_jump() { return tune().k3_variant != 16; }     // 16 = the round-1 single-chain walk, for A/B runs
@@ -63,7 +59,7 @@ static bool hc_jump() { return tune().k3_variant != 16; }     // 16 = the round-
 // a single small block needs a few MiB, not gigabytes
 size_t hc_work_bytes(int num_sms, uint32_t nblocks) {
     const size_t ctas = (nblocks + HC_WARPS - 1) / HC_WARPS, max_ctas = (size_t)num_sms * HC_CTAS_PER_SM;
-    return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * (sizeof(HcWorkJ) > sizeof(HcWork) ? sizeof(HcWorkJ) : sizeof(HcWork));
+    return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * sizeof(HcWork);
 }
 
 __device__ __forceinline__ uint32_t hashHC(uint32_t v) { return (v * HASH_MULTIPLIER) >> 17; }  // :129-131
@@ -151,8 +147,8 @@ __device__ __forceinline__ uint32_t eval_candidate(const uint8_t* __restrict__ s
 template <bool JUMP>
 __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t cap,
                                   void* wv, int nbs, uint32_t jump_after, uint32_t lane, uint32_t& olen, int& st) {
-    HcWork* w = reinterpret_cast<HcWork*>(wv);                 // hash[] first and `base` are read through the variant's type
-    HcWorkJ* wj = reinterpret_cast<HcWorkJ*>(wv);
+    HcWork* w = reinterpret_cast<HcWork*>(wv);
+    HcWork* wj = w;
     st = ST_OK;
     olen = 0;
     if (n == 0) return;                                                  // :1443
@@ -167,7 +163,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
         return;
     }
     // epoch base for this block's bucket values
-    uint32_t* basep = JUMP ? &wj->base : &w->base;
+    uint32_t* basep = &w->base;
     uint32_t base = *basep;
     if (base > 0xFFFFFFFFu - n - 16u) {   // would wrap: re-zero once
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -178,12 +174,13 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     __syncwarp();
     if (lane == 0) *basep = base + n;
     uint32_t* H = w->hash;
-    uint16_t* C = JUMP ? wj->jump[0] : w->chain;
+    uint16_t* C = w->jump[0];
     const bool patternAnalysis = nbs > 128;                              // :983
     const uint32_t mflimit = n - MFLIMIT, mlimit = n - LASTLITERALS;
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
     uint32_t ip = 0, ntu = 0;
     bool jm = false;                       // jump mode on
+    uint32_t jv = 0;                       // jump mode: positions below jv have their jump levels (built lazily, in bulk)
     uint32_t nsearch = 0, nhops = 0, dsum = 0;   // chain statistics while it is off: searches, hops, sum of hop distances / 256
 
     while (ip <= mflimit) {                                              // :1009
@@ -208,25 +205,6 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                 if ((peers & gt) == 0) H[h] = base + idx;
             }
             __syncwarp();
-            if (JUMP && jm) {
-                // distance to the 2nd, 4th, 8th, 16th predecessor: level k = level k-1 here + level k-1 at that predecessor
-                // (already complete: an earlier position, or a lane of this batch that wrote it one step ago); 65535 =
-                // "out of reach", as in the reference's clamp (:505)
-                uint32_t dk = delta;
-#pragma unroll
-                for (int k = 1; k < HC_LEVELS; k++) {
-                    uint32_t nd = MAX_DISTANCE;
-                    if (act) {
-                        if (dk < MAX_DISTANCE && dk <= idx) {
-                            const uint32_t sum = dk + wj->jump[k - 1][(idx - dk) & (HC_CHAIN - 1)];
-                            nd = sum > MAX_DISTANCE ? MAX_DISTANCE : sum;
-                        }
-                        wj->jump[k][idx & (HC_CHAIN - 1)] = (uint16_t)nd;
-                    }
-                    __syncwarp();
-                    dk = nd;
-                }
-            }
             ntu += 32;
         }
         ntu = ip;
@@ -242,6 +220,35 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
         if (m != 0) {                                                        // :566
             uint32_t final_m = m;
             if (JUMP && jm) {
+                if (m >= jv) {
+                    // The chain starts in the tail that has no jump levels yet: build them for every position a search can
+                    // still reach, oldest first — level k = level k-1 here + level k-1 at that predecessor (an earlier
+                    // position, complete; or a lane of this batch, written one step ago); 65535 = "out of reach", as in
+                    // the reference's clamp (:505).  Predecessors below `lo` are out of every later search's reach,
+                    // whatever their stale entries say, and so is everything reached through them.  Done lazily and in
+                    // bulk because the four dependent reads per batch are only worth paying for positions a chain
+                    // actually enters (incompressible stretches insert one position per search and never do).
+                    const uint32_t lo = ip > MAX_DISTANCE ? ip - MAX_DISTANCE : 0;
+                    for (uint32_t b0 = jv > lo ? jv : lo; b0 < ip; b0 += 32) {
+                        const uint32_t idx = b0 + lane;
+                        const bool act = idx < ip;
+                        uint32_t dk = act ? (uint32_t)C[idx & (HC_CHAIN - 1)] : MAX_DISTANCE;
+#pragma unroll
+                        for (int k = 1; k < HC_LEVELS; k++) {
+                            uint32_t nd = MAX_DISTANCE;
+                            if (act) {
+                                if (dk < MAX_DISTANCE && dk <= idx) {
+                                    const uint32_t sum = dk + wj->jump[k - 1][(idx - dk) & (HC_CHAIN - 1)];
+                                    nd = sum > MAX_DISTANCE ? MAX_DISTANCE : sum;
+                                }
+                                wj->jump[k][idx & (HC_CHAIN - 1)] = (uint16_t)nd;
+                            }
+                            __syncwarp();
+                            dk = nd;
+                        }
+                    }
+                    jv = ip;
+                }
                 // chain positions P_0 = m, P_{i+1} = P_i - chain[P_i] (:619-621), 32 per round: lane j jumps from the
                 // round's first position by the bits of j.  A position is visited while it is > 0 (:571), within
                 // 65535 of ip (:573) and attempts are left; positions only decrease, so the visited lanes are a prefix.
@@ -324,28 +331,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                 // long chains whose hops land far apart (each one a DRAM round trip): text.  Chains of near neighbours
                 // (records with a repeated field: hops of a few dozen positions, served by L1/L2) are faster walked as they are.
                 if (nsearch >= 64 && nhops > jump_after * nsearch && dsum > 2 * nhops) {
-                    // long chains: build the jump levels of every position a later search can still reach, oldest first
-                    // (a level reads the level below at a predecessor; predecessors below `lo` are out of every later
-                    // search's reach, whatever their stale entries say, and so is everything reached through them)
-                    const uint32_t lo = ip > MAX_DISTANCE ? ip - MAX_DISTANCE : 0;
-                    for (uint32_t b0 = lo; b0 < ip; b0 += 32) {
-                        const uint32_t idx = b0 + lane;
-                        const bool act = idx < ip;
-                        uint32_t dk = act ? (uint32_t)C[idx & (HC_CHAIN - 1)] : MAX_DISTANCE;
-#pragma unroll
-                        for (int k = 1; k < HC_LEVELS; k++) {
-                            uint32_t nd = MAX_DISTANCE;
-                            if (act) {
-                                if (dk < MAX_DISTANCE && dk <= idx) {
-                                    const uint32_t sum = dk + wj->jump[k - 1][(idx - dk) & (HC_CHAIN - 1)];
-                                    nd = sum > MAX_DISTANCE ? MAX_DISTANCE : sum;
-                                }
-                                wj->jump[k][idx & (HC_CHAIN - 1)] = (uint16_t)nd;
-                            }
-                            __syncwarp();
-                            dk = nd;
-                        }
-                    }
+                    jv = 0;                                   // nothing has levels yet: the first search that needs them builds them
                     jm = true;
                 }
             }
@@ -419,7 +405,7 @@ __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in
                                                                uint8_t* work, uint32_t* ticket, uint32_t jump_after) {
     const uint32_t lane = lane_id();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    void* w = work + (size_t)gw * (JUMP ? sizeof(HcWorkJ) : sizeof(HcWork));
+    void* w = work + (size_t)gw * sizeof(HcWork);
     for (;;) {
         uint32_t blk = 0;
         if (lane == 0) blk = atomicAdd(ticket, 1u);
@@ -446,7 +432,7 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     const int cap_ctas = tune().k3_variant;                 // experiment: 1..8 = at most this many CTAs (of 4 warps) per SM
     const bool jump = hc_jump() && nb_searches > 32;         // chains of at most 32 hops never earn the tables back
     // a block switches to jump mode when its searches average more than this many chain hops (spare1 overrides: experiments)
-    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 24u;
+    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 16u;
 #define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket, jump_after)
     if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
         const uint32_t g = (uint32_t)(num_sms * cap_ctas);
