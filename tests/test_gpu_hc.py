@@ -83,3 +83,23 @@ def test_hc_frames_and_records(z, oracle, ctx):
     for i in range(64):
         want = oracle.compress_hc(recs[offs[i]:offs[i] + 4096], 9)
         assert st[i] == 0 and dst[doffs[i]:doffs[i] + int(ol[i])].tobytes() == want, i
+
+
+def test_hc_levels_interleaved_on_one_workspace(z, oracle):
+    """The HC work areas persist between calls (epoch-tagged tables, nothing re-zeroed): every kernel variant — the
+    single-chain walk of levels <= 6, the jump-table walk of levels 7..9, before and after a block has switched to jump
+    mode — must leave them in a state the next one reads correctly.  Text blocks have long, far-apart chains (jump mode),
+    binary ones long near chains (stay in chain mode), mixed ones switch part-way."""
+    from zig_lz4_b200 import datagen
+    blocks = [datagen.generate(262144, mode=m, seed=s).tobytes() for m, s in ((0, 11), (1, 12), (4, 13), (2, 14), (0, 15))]
+    for rnd in range(2):
+        for level in (9, 3, 7, 6, 9, 8, 4, 9):
+            for b in blocks:
+                assert z.lz4hc.compressHC(b, level) == oracle.compress_hc(b, level), (rnd, level)
+    # a batch of many blocks at once (several work areas), then single blocks again on the same areas
+    big = datagen.generate(16 << 20, mode=0, seed=21).tobytes()
+    zp = z.lz4f.Preferences(blockSizeID=5, blockMode=1, compressionLevel=9)
+    op = oracle.make_prefs(block_size_id=5, block_mode=1, compression_level=9)
+    assert z.lz4f.compressFrame(big, zp) == oracle.compress_frame(big, op, threads=8)
+    for level in (5, 9):
+        assert z.lz4hc.compressHC(blocks[0], level) == oracle.compress_hc(blocks[0], level)

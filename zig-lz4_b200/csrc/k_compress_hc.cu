@@ -181,7 +181,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     uint32_t ip = 0, ntu = 0;
     bool jm = false;                       // jump mode on
     uint32_t jv = 0;                       // jump mode: positions below jv have their jump levels (built lazily, in bulk)
-    uint32_t nsearch = 0, nhops = 0, dsum = 0;   // chain statistics while it is off: searches, hops, sum of hop distances / 256
+    uint32_t nsearch = 0, nhops = 0, dsum = 0;   // chain statistics of the current window of searches: count, hops, hop distance / 256
 
     while (ip <= mflimit) {                                              // :1009
         // ---------------- insertHC(ctx, ip): positions [ntu, ip), :491-510 ----------------
@@ -276,6 +276,10 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                     }
                     const uint32_t sm = __ballot_sync(FULL, stuck);
                     if (sm) cnt = (uint32_t)__ffs(sm);                                           // that position is still a candidate
+                    if (cnt) {                                                                   // window statistics
+                        nhops += cnt;
+                        dsum += (basepos - __shfl_sync(FULL, pos, cnt - 1)) >> 8;
+                    }
                     const uint32_t my_cand = pos;
                     uint32_t len = 0;
                     if (lane < cnt) len = eval_candidate(src, ip, my_cand, pattern, f1, f2, f3, mlimit);   // :586-591
@@ -325,16 +329,15 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
                 }
                 if (xm) { done = true; final_m = __shfl_sync(FULL, my_cand, X); }
             }
-            if (JUMP) {
-                nsearch++;
-                nhops += (uint32_t)(nbs - attempts);
-                // long chains whose hops land far apart (each one a DRAM round trip): text.  Chains of near neighbours
-                // (records with a repeated field: hops of a few dozen positions, served by L1/L2) are faster walked as they are.
-                if (nsearch >= 64 && nhops > jump_after * nsearch && dsum > 2 * nhops) {
-                    jv = 0;                                   // nothing has levels yet: the first search that needs them builds them
-                    jm = true;
-                }
+            if (JUMP) nhops += (uint32_t)(nbs - attempts);
             }
+            if (JUMP && ++nsearch == 128) {
+                // Every 128 searches: jump mode pays for long chains whose hops land far apart (each one a DRAM round
+                // trip): text.  Chains of near neighbours (records with a repeated field: hops of a few dozen positions,
+                // served by L1/L2), short chains and incompressible stretches are faster walked as they are.  Positions
+                // inserted while the mode is off simply have no levels yet (jv stays where it is).
+                jm = nhops > jump_after * nsearch && dsum > 2 * nhops;
+                nsearch = nhops = dsum = 0;
             }
             if (patternAnalysis) {                                                               // :626
                 uint32_t delta = C[final_m & (HC_CHAIN - 1)];
@@ -432,7 +435,7 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     const int cap_ctas = tune().k3_variant;                 // experiment: 1..8 = at most this many CTAs (of 4 warps) per SM
     const bool jump = hc_jump() && nb_searches > 32;         // chains of at most 32 hops never earn the tables back
     // a block switches to jump mode when its searches average more than this many chain hops (spare1 overrides: experiments)
-    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 16u;
+    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 24u;
 #define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket, jump_after)
     if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
         const uint32_t g = (uint32_t)(num_sms * cap_ctas);
