@@ -636,7 +636,7 @@ int b2_decompress_dev_impl(b2lz4_ctx* c, const void* srcv, size_t n, void* dstv,
         B2_CUDA(cudaMemcpyAsync(c->pin_aux.p, src + w.end_pos, 4, cudaMemcpyDeviceToHost, s));
     }
     T.mark(5);
-    B2_CUDA(cudaStreamSynchronize(s));
+    if (cc || c->timing) B2_CUDA(cudaStreamSynchronize(s));   // (without a content checksum the summary read-back was the last device work)
     if (c->timing) {
         cudaEventElapsedTime(&c->phase_ms[2], c->ev_t[0], c->ev_t[1]);  // header + walk
         cudaEventElapsedTime(&c->phase_ms[1], c->ev_t[1], c->ev_t[2]);  // block checksums
