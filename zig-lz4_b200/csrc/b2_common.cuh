@@ -1,7 +1,11 @@
 // b2_common.cuh — shared device helpers for the LZ4 kernels (sm_100a).
 #pragma once
 #include <cstdint>
+#ifdef B2_EMU   // host build of the device code for the one-warp emulator (tools/warp_emu): test tooling only
+#include "emu_cuda.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace b2 {
 
@@ -68,6 +72,10 @@ struct OutSet {
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+#ifdef B2_EMU
+__device__ __forceinline__ uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
+__device__ __forceinline__ uint32_t lanemask_gt() { return lane_id() == 31 ? 0u : ~((2u << lane_id()) - 1u); }
+#else
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -78,6 +86,7 @@ __device__ __forceinline__ uint32_t lanemask_gt() {
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
     return m;
 }
+#endif
 
 // Unaligned little-endian u32 from read-only global memory (input streams): two aligned words
 // through the non-coherent path + funnel shift.  Never touches a word that holds no valid byte.

@@ -26,12 +26,22 @@
 // shared memory: u16 entries when every block is <= 64 KiB (8 KiB/warp), u32 otherwise (16 KiB/warp).
 // Blocks are handed to warps through a global ticket so long and short blocks balance.
 #include "b2_common.cuh"
+#ifndef B2_EMU
 #include "b2_kernels.h"
 #include <mutex>
+#endif
 
 namespace b2 {
 
 constexpr int HASH_ENTRIES = 4096;  // LZ4_HASH_SIZE_U32, src/lz4.zig:33
+
+#ifdef B2_EMU   // counters of the host emulation (tools/warp_emu/emu_k1.cpp); nothing on the device
+struct EmuStats { uint64_t windows, fast_windows, bailed_windows, sequences, batched_sequences; };
+extern EmuStats g_emu_stats;
+#define EMU_COUNT(field, n) do { if (lane == 0) g_emu_stats.field += (n); } while (0)
+#else
+#define EMU_COUNT(field, n) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * HASH_MULTIPLIER) >> 20; }  // :75-77
 
@@ -43,8 +53,13 @@ __device__ __forceinline__ uint32_t ld_u32x(const uint8_t* __restrict__ p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
     return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
 }
+#ifdef B2_EMU
+__device__ __forceinline__ void prefetch_l1(const void*) {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 // F(x) = sum_{u<x} (u >> 6): cumulative step of the reference's `step = searchMatchNb >> 6` schedule.
 __device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
     uint32_t A = x >> 6, B = x & 63;
@@ -59,6 +74,15 @@ __device__ __forceinline__ uint32_t step_prefix(uint32_t x) {
 // been waited for, and everything in flight is drained before the warp leaves the kernel.
 constexpr uint32_t RING_LINE = 128, RING_SLOTS = 4, RING_BYTES = RING_LINE * RING_SLOTS;
 
+#ifdef B2_EMU   // the ring variant is not emulated (RING = false there): empty stand-ins for its PTX
+__device__ __forceinline__ uint32_t smem_addr(const void*) { return 0; }
+__device__ __forceinline__ void mbar_init(uint32_t, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t, uint32_t) {}
+__device__ __forceinline__ void bulk_load(uint32_t, const void*, uint32_t, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint32_t, uint32_t) {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t) { return 0; }
+#else
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -74,6 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
                  "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a));
+    return w;
+}
+#endif
 
 struct Ring {
     uint32_t data;      // shared-memory address of this warp's RING_BYTES
@@ -113,7 +144,7 @@ struct Ring {
             if (g1 > g0) {
                 __syncwarp();                                        // every lane is done reading the line this replaces
                 if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fence_proxy_async();
                     mbar_expect_tx(bars + 8 * s, (uint32_t)(g1 - g0));
                     bulk_load(data + (uint32_t)(g0 & (RING_BYTES - 1)), reinterpret_cast<const void*>(g0), (uint32_t)(g1 - g0),
                               bars + 8 * s);
@@ -132,9 +163,7 @@ struct Ring {
     // unaligned little-endian u32 at global address a (its line(s) ensured)
     __device__ __forceinline__ uint32_t read_u32(uint64_t a) const {
         const uint32_t o = (uint32_t)a & (RING_BYTES - 1);
-        uint32_t w0, w1;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(data + (o & ~3u)));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(data + ((o + 4) & (RING_BYTES - 4))));
+        const uint32_t w0 = lds_u32(data + (o & ~3u)), w1 = lds_u32(data + ((o + 4) & (RING_BYTES - 4)));
         return __funnelshift_r(w0, w1, (o & 3u) * 8);
     }
 };
@@ -357,14 +386,22 @@ __device__ __forceinline__ bool emit_sequence(const uint8_t* __restrict__ src, u
         {
             const uint32_t need = (!lit_in_lanes && t < 0) ? 1u : 0u;   // literals not in the window's registers (chained window)
             const uint8_t* lp = src + anchor + (lane ? lane - 1 : 0);
+#ifdef B2_EMU
+            if (need) bv = *lp;
+#else
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u8 %0, [%2];\n\t}"
                 : "+r"(bv) : "r"(need), "l"(reinterpret_cast<uint64_t>(lp)));   // src is global memory (asserted by the kernel): its generic address IS its global address
+#endif
         }
         const uint32_t ob = t == 0 ? offset : offset >> 8;
         bv = t >= 0 ? ob : bv;
         bv = lane == 0 ? ((LL << 4) | ml) : bv;
+#ifdef B2_EMU
+        if (t < 2) dst[op + lane] = (uint8_t)bv;
+#else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %0, 2;\n\t@p st.global.u8 [%1], %2;\n\t}"
                      :: "r"(t), "l"(reinterpret_cast<uint64_t>(dst + op + lane)), "r"(bv) : "memory");
+#endif
         op = seq_end;
     } else {
         // the caller computes the size itself, so that `op` never depends on a call result
@@ -424,6 +461,27 @@ __device__ __forceinline__ uint32_t extend_match(const uint8_t* __restrict__ src
 }
 
 __device__ __forceinline__ uint32_t lane_range(uint32_t a, uint32_t b) { return ((2u << b) - 1u) & ~((1u << a) - 1u); }
+
+// Writes the short sequences a window's walk has marked, all at once.  M: their match lanes; Lit: their literal lanes
+// (the run of lanes before each match lane; lane = window position, its byte is the low byte of its word `v`); a match
+// lane holds offset | ml << 16 in `mseq`.  Sequence k is token | literals | offset (src/lz4.zig:362-432 without length
+// bytes: LL < 15, ml < 15), so a lane's output position is op + literals before it + 3 per match lane before it + 1.
+// Returns false if the batch does not fit (nothing is written then).
+__device__ __forceinline__ bool flush_batch(uint8_t* __restrict__ dst, uint32_t cap, uint32_t& op, uint32_t M, uint32_t Lit,
+                                            uint32_t v, uint32_t mseq, uint32_t lane, uint32_t lt) {
+    const uint32_t total = (uint32_t)__popc(Lit) + 3u * (uint32_t)__popc(M);
+    if (op + total > cap) return false;
+    uint8_t* o = dst + op + (uint32_t)__popc(Lit & lt) + 3u * (uint32_t)__popc(M & lt) + 1u;
+    if ((Lit >> lane) & 1u) o[0] = (uint8_t)v;
+    if ((M >> lane) & 1u) {
+        const uint32_t LL = lane + (uint32_t)__clz(~Lit & lt) - 32u;     // literal lanes right before this one
+        o[0] = (uint8_t)mseq;
+        o[1] = (uint8_t)(mseq >> 8);
+        *(o - LL - 1) = (uint8_t)((LL << 4) | (mseq >> 16));
+    }
+    op += total;
+    return true;
+}
 
 // The search of compress_block_a1 past its first window: reference iterations j0, j0+1, ... of the search that started
 // at q (acceleration 1: step = iteration >> 6, :329-333), 32 per round, until a match (returns its position, the
@@ -487,16 +545,65 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
         uint32_t e = 0;  // last put() position; the search starts at e + 1 (0: nothing put, table value 0 == empty)
         const uint64_t ga = reinterpret_cast<uint64_t>(src);
         if (RING) ring.begin_block(ga, n);
+        // Forward words in registers (not in the TMA ring variant): the 32 random candidate sectors every window of
+        // every warp pulls through the SM's small L1 (the tables take the shared-memory side of it) evict the input
+        // lines before the next window comes back to them, so the window's own words used to cost an L2 round trip
+        // before the table could even be asked.  Lane j now holds the aligned input word whose index is congruent
+        // to j mod 32, of the 32 words from `wlo` on; a window takes its words from there with shuffles; the slots of the
+        // words the window has moved past are re-targeted 128 bytes further and loaded while the window is worked on.
+        // Only a jump over more than 56 bytes waits for memory.
+        const uint32_t* const w0p = reinterpret_cast<const uint32_t*>(ga & ~uint64_t(3));   // word that holds src[0]
+        uint32_t W = 0, wlo = 0xFFFFFF00u;
 
         while (e + 1 < lim) {                                    // :320 with ip == e + 1
             if (RING) ring.ensure(ga + e, lane);
-            else if (lane == 0 && e + 512 < n) prefetch_l1(src + e + 512);
+            else if (lane == 0 && e + 1024 < lim) prefetch_l2(src + e + 1024);
             // ---------------- window: p = base + lane ----------------
             const uint32_t base = e;
             const uint32_t p = base + lane;
+            EMU_COUNT(windows, 1);
             const bool inwin = p <= lim;                         // positions the walk may touch (p + 3 <= n - 9)
             uint32_t v = 0, h = 0x80000000u | lane, old = 0;
-            if (inwin) { v = RING ? ring.read_u32(ga + p) : ld_u32x(src + p); h = hash4(v); old = table[h]; }
+            uint32_t F1, F2, F3;                                 // the words at p + 4, p + 8, p + 12 (for the extension)
+            if (RING) {
+                uint32_t v2 = 0;
+                if (inwin) v = ring.read_u32(ga + p);
+                if (lane < 16 && p + 32 <= lim) v2 = ring.read_u32(ga + p + 32);
+                const uint32_t a1 = __shfl_sync(FULL, v, lane + 4), b1 = __shfl_sync(FULL, v2, lane + 4);
+                const uint32_t a2 = __shfl_sync(FULL, v, lane + 8), b2 = __shfl_sync(FULL, v2, lane + 8);
+                const uint32_t a3 = __shfl_sync(FULL, v, lane + 12), b3 = __shfl_sync(FULL, v2, lane + 12);
+                F1 = lane + 4 < 32 ? a1 : b1; F2 = lane + 8 < 32 ? a2 : b2; F3 = lane + 12 < 32 ? a3 : b3;
+            } else {
+                // (recomputed from the pointer and lim every window: as block constants they were spilled, and a spill
+                // reload goes through the same L1 the candidate reads keep flushing)
+                uint32_t a0 = (uint32_t)ga, limv = lim;
+#ifndef B2_EMU
+                asm volatile("" : "+r"(a0), "+r"(limv));
+#endif
+                a0 &= 3u;
+                const uint32_t nwords = (a0 + limv + MFLIMIT + 3) >> 2;      // words holding bytes of the block: nothing beyond is read
+                const uint32_t i0 = (a0 + base) >> 2;
+                if (i0 - wlo > 14u) {                                        // (also i0 < wlo): not covered, fetch and wait
+                    wlo = i0;
+                    const uint32_t idx = i0 + ((lane - i0) & 31u);
+                    W = idx < nwords ? __ldg(w0p + idx) : 0u;
+                }
+                const uint32_t ab = ((a0 + base) & 3u) + lane;               // byte offset from word i0
+                const uint32_t sl = i0 + (ab >> 2), sh = (ab & 3u) * 8u;
+                const uint32_t x0 = __shfl_sync(FULL, W, sl), x1 = __shfl_sync(FULL, W, sl + 1), x2 = __shfl_sync(FULL, W, sl + 2),
+                               x3 = __shfl_sync(FULL, W, sl + 3), x4 = __shfl_sync(FULL, W, sl + 4);
+                if (inwin) v = __funnelshift_r(x0, x1, sh);
+                F1 = __funnelshift_r(x1, x2, sh); F2 = __funnelshift_r(x2, x3, sh); F3 = __funnelshift_r(x3, x4, sh);
+                if (i0 != wlo) {
+                    // slide: the slots of words [wlo, i0) take [wlo + 32, i0 + 32).  Loaded straight into W: nothing reads W
+                    // before the next window's shuffles, a whole window's work away.
+                    const uint32_t r = (lane - wlo) & 31u;
+                    const uint32_t idx = wlo + 32u + r;
+                    if (r < i0 - wlo) W = idx < nwords ? __ldg(w0p + idx) : 0u;
+                    wlo = i0;
+                }
+            }
+            if (inwin) { h = hash4(v); old = table[h]; }
             const uint32_t peers = __match_any_sync(FULL, h);
             bool vold = inwin && old > 0 && old + MAX_DISTANCE >= p;     // :345-347 (old < e <= p always)
             // One 16-byte read at the candidate serves the 4-byte compare (:348) and stages the next
@@ -523,12 +630,6 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             // the 16 positions after it (v2).  mlpk = length | "bytes exhausted, continue from memory" << 8.
             uint32_t mlpk;
             {
-                uint32_t v2 = 0;
-                if (lane < 16 && p + 32 <= lim) v2 = RING ? ring.read_u32(ga + p + 32) : ld_u32x(src + p + 32);
-                const uint32_t a1 = __shfl_sync(FULL, v, lane + 4), b1 = __shfl_sync(FULL, v2, lane + 4);
-                const uint32_t a2 = __shfl_sync(FULL, v, lane + 8), b2 = __shfl_sync(FULL, v2, lane + 8);
-                const uint32_t a3 = __shfl_sync(FULL, v, lane + 12), b3 = __shfl_sync(FULL, v2, lane + 12);
-                const uint32_t F1 = lane + 4 < 32 ? a1 : b1, F2 = lane + 8 < 32 ? a2 : b2, F3 = lane + 12 < 32 ? a3 : b3;
                 uint32_t nfw = inwin ? (lim - p) >> 2 : 0u;              // forward words at positions <= lim
                 nfw = nfw < 3 ? nfw : 3;
                 const uint32_t navail = 4 * nfw < nmb ? 4 * nfw : nmb;
@@ -544,7 +645,58 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             const bool plt = p < lim;           // (implies inwin)
             uint32_t lo = 0, V = 1u;            // lane `lo`: last put(); V: lanes the reference has visited
             bool finish = false, more = false;  // finish: the block's search loop is over; more: search continues past lane 31
+            // Short sequences whose literals sit in the window's lanes are not written one by one: the walk only marks
+            // them (M: their match lanes, Lit: their literal lanes; a match lane keeps offset | ml << 16 in `mseq`) and
+            // flush_batch writes all of them at once.
+            uint32_t M = 0, Lit = 0;
+            uint32_t mseq = ((p - old) & 0xFFFFu) | ((mlpk & 0xFFu) << 16);    // as a match against the table candidate
+            // Static chain: a lane without an earlier lane of its bucket in this window sees the table as it was before
+            // the window whatever the walk visits, so its candidate (old), its validity (vold) and its length (mlpk) are
+            // known now.  J answers, for the search that starts after this lane (this lane = `lo`): where is the next
+            // match and where does it end — if that is decided statically (next candidate is such a lane, fully measured,
+            // fewer than 15 literals); everything else (J_SLOW) goes through the general step below.  Only in windows far
+            // from the block's end (every lane eligible, no exit at :335, match ends < lim).
+            constexpr uint32_t J_NONE = 0x10000u, J_SLOW = 0x20000u;
+            const bool fast_ok = base + 64 <= lim;
+            uint32_t J = J_SLOW;
+            if (fast_ok) {
+                const bool hasprev = (peers & lt) != 0;
+                const uint32_t Cm = __ballot_sync(FULL, hasprev || vold);             // lanes that may be a match
+                const uint32_t Sm = __ballot_sync(FULL, !hasprev && vold && (mlpk >> 8) == 0);   // ... decided statically
+                const uint32_t nx = Cm & gt;
+                const uint32_t nl = nx ? (uint32_t)__ffs(nx) - 1 : lane;
+                const uint32_t mlen = __shfl_sync(FULL, mlpk & 0xFFu, nl);
+                const bool slow = ((Sm >> nl) & 1u) == 0 || nl - lane >= RUN_MASK;
+                J = nx == 0 ? J_NONE : (slow ? J_SLOW : ((nl + MINMATCH + mlen) | (nl << 8)));
+            }
             for (;;) {
+                if (fast_ok && anchor == base + lo) {
+                    bool window_done = false;
+                    for (;;) {
+                        const uint32_t j = __shfl_sync(FULL, J, lo);
+                        if (j & (J_NONE | J_SLOW)) {
+                            if (j & J_NONE) { V |= ~((2u << lo) - 1u); more = true; window_done = true; }   // as `m == 0` below
+                            break;
+                        }
+                        const uint32_t L = (j >> 8) & 31u, mendl = j & 0xFFu;
+                        EMU_COUNT(sequences, 1);
+                        EMU_COUNT(batched_sequences, 1);
+                        M |= 1u << L;
+                        const uint32_t lr = lane_range(lo, L - 1);
+                        Lit |= lr;
+                        V |= lr << 1;
+                        if (mendl >= 31) {                                   // (mend < lim: fast_ok)
+                            e = base + mendl;
+                            anchor = e;
+                            window_done = true;
+                            break;
+                        }
+                        lo = mendl;
+                        V |= 1u << lo;
+                        anchor = base + lo;
+                    }
+                    if (window_done) break;
+                }
                 // lanes lo+1.. are iterations 1.. of the search that starts at e + lo + 1 (< lim)
                 const bool elig = lane > lo && (plt || (inwin && lane == lo + 2));
                 // candidate: nearest earlier lane of the same bucket that has been visited when this lane is probed
@@ -563,6 +715,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 const uint32_t L = (uint32_t)__ffs(m) - 1;
                 V |= lane_range(lo + 1, L);
                 const uint32_t mpos = base + L;
+                EMU_COUNT(sequences, 1);
                 // blocks <= 64 KiB (u16 table): candidate position and its pre-measured extension travel in one shuffle
                 uint32_t mcand, pk;
                 if (sizeof(TableT) == 2) {
@@ -581,10 +734,20 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 } else {                                                 // candidate inside the window (runs, short periods)
                     ml = extend_bytes(src, mpos + MINMATCH, mcand + MINMATCH, mlimit, lane);
                 }
-                const uint32_t litb = __shfl_sync(FULL, v, lo + lane - 1) & 0xFFu;   // lane t (1..LL): src[anchor + t - 1]
-                if (!emit_sequence<TableT>(src, dst, cap, op, anchor, LL, ml, mpos - mcand, anchor == base + lo, litb, lane)) {
-                    st = ST_OUTPUT_TOO_SMALL;
-                    return;
+                if (anchor == base + lo && LL < RUN_MASK && ml < ML_MASK) {
+                    M |= 1u << L;                                        // joins the batch
+                    Lit |= lane_range(lo, L - 1);
+                    if (lane == L) mseq = (mpos - mcand) | (ml << 16);
+                } else {
+                    // long form, or literals that start before the window: written now, after what is pending
+                    if (M) {
+                        if (!flush_batch(dst, cap, op, M, Lit, v, mseq, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
+                        M = 0; Lit = 0;
+                    }
+                    if (!emit_sequence<TableT>(src, dst, cap, op, anchor, LL, ml, mpos - mcand, false, 0, lane)) {
+                        st = ST_OUTPUT_TOO_SMALL;
+                        return;
+                    }
                 }
                 const uint32_t mend = mpos + MINMATCH + ml;
                 anchor = mend;                                           // :435
@@ -596,6 +759,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 V |= 1u << lo;
                 if (mend + 1 >= lim) { finish = true; break; }           // :320
             }
+            if (M && !flush_batch(dst, cap, op, M, Lit, v, mseq, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
             // ---------------- table after the window: last visited lane of every bucket, else unchanged ----------------
             {
                 const uint32_t vg = peers & V;
@@ -650,6 +814,7 @@ __device__ __forceinline__ void compress_block(const uint8_t* __restrict__ src, 
     else compress_block_general<TableT>(src, n, dst, cap, table, accel, lane, olen, st);
 }
 
+#ifndef B2_EMU
 // WARPS warps per CTA, CTAS CTAs per SM.  RING: one CTA per SM whose warps also own a forward input ring.
 template <typename TableT, bool RING, int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_compress_fast(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
@@ -707,8 +872,8 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
     if (e != cudaSuccess) return e;
     const bool small = max_len <= 65536;
     // shared memory per SM is what bounds the blocks in flight (227 KiB per CTA, 228 per SM, 1 KiB reserved per CTA):
-    //   u16 tables (8 KiB / warp):  CTAs of 3 warps, 9 per SM -> 27 blocks in flight
-    //   u32 tables (16 KiB / warp): CTAs of 1 warp, 13 per SM -> 13 blocks in flight
+    //   u16 tables (8 KiB / warp):  CTAs of 7 warps, 4 per SM -> 28 blocks in flight (k1_variant 1: 3 warps, 9 per SM -> 27)
+    //   u32 tables (16 KiB / warp): CTAs of 7 warps, 2 per SM -> 14 blocks in flight (k1_variant 1: 1 warp, 13 per SM -> 13)
     //   ring variant (b2lz4_debug_tune("k1_variant", 2)): ONE CTA per SM of 26 (u16) / 13 (u32) warps, each with its table,
     //   a 512-byte forward input ring fed by TMA bulk copies and four mbarriers
     const Tune& t = tune();
@@ -723,6 +888,8 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
         };
         set((const void*)k_compress_fast<uint16_t, false, 3, 9>, 3 * HASH_ENTRIES * 2);
         set((const void*)k_compress_fast<uint32_t, false, 1, 13>, HASH_ENTRIES * 4);
+        set((const void*)k_compress_fast<uint16_t, false, 7, 4>, 7 * HASH_ENTRIES * 2);
+        set((const void*)k_compress_fast<uint32_t, false, 7, 2>, 7 * HASH_ENTRIES * 4);
         set((const void*)k_compress_fast<uint16_t, true, 26, 1>, 26 * (HASH_ENTRIES * 2 + (int)RING_BYTES + (int)RING_SLOTS * 8));
         set((const void*)k_compress_fast<uint32_t, true, 13, 1>, 13 * (HASH_ENTRIES * 4 + (int)RING_BYTES + (int)RING_SLOTS * 8));
     });
@@ -733,7 +900,8 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
         uint32_t grid = want < (uint32_t)num_sms ? want : (uint32_t)num_sms;
         if (small) k_compress_fast<uint16_t, true, 26, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
         else k_compress_fast<uint32_t, true, 13, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
-    } else {
+    } else if (t.k1_variant == 1) {
+        // the round-1/2 shape (27 / 13 blocks per SM), kept for A/B measurements
         const int warps = small ? 3 : 1;
         int ctas_per_sm = small ? 9 : 13;
         if (t.k1_ctas > 0 && t.k1_ctas < ctas_per_sm) ctas_per_sm = t.k1_ctas;   // occupancy experiments
@@ -743,9 +911,22 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
         uint32_t grid = want < maxg ? want : maxg;
         if (small) k_compress_fast<uint16_t, false, 3, 9><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
         else k_compress_fast<uint32_t, false, 1, 13><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+    } else {
+        // 7-warp CTAs: 4 per SM with u16 tables (4 x (56 + 1) KiB = all 228 KiB of the SM: 28 blocks in flight, 72 registers),
+        // 2 per SM with u32 tables (14 blocks in flight)
+        const int warps = 7;
+        int ctas_per_sm = small ? 4 : 2;
+        if (t.k1_ctas > 0 && t.k1_ctas < ctas_per_sm) ctas_per_sm = t.k1_ctas;
+        const size_t smem = (size_t)warps * HASH_ENTRIES * (small ? sizeof(uint16_t) : sizeof(uint32_t));
+        uint32_t want = (nblocks + warps - 1) / warps;
+        uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
+        uint32_t grid = want < maxg ? want : maxg;
+        if (small) k_compress_fast<uint16_t, false, 7, 4><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        else k_compress_fast<uint32_t, false, 7, 2><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     }
     count_launch();
     return cudaGetLastError();
 }
+#endif  // !B2_EMU
 
 }  // namespace b2
