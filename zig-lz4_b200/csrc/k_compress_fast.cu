@@ -554,6 +554,12 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
         // Only a jump over more than 56 bytes waits for memory.
         const uint32_t* const w0p = reinterpret_cast<const uint32_t*>(ga & ~uint64_t(3));   // word that holds src[0]
         uint32_t W = 0, wlo = 0xFFFFFF00u;
+        // Large blocks (u32 tables: few warps per SM, a block's own latency is what counts, registers to spare): the batch
+        // of a window is written while the NEXT window waits for its candidate reads (the one long wait of a window);
+        // pM / pLit / ppk (literal byte | mseq << 8 per lane) hold it until then.  4 MiB text blocks 136 -> 127 ms.  With
+        // u16 tables (72 registers, 28 warps per SM hide the wait) the deferral only costs a spill: 15.9 -> 16.3 ms per GiB.
+        constexpr bool DEFER = sizeof(TableT) == 4;
+        uint32_t pM = 0, pLit = 0, ppk = 0;
 
         while (e + 1 < lim) {                                    // :320 with ip == e + 1
             if (RING) ring.ensure(ga + e, lane);
@@ -609,13 +615,19 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
             // One 16-byte read at the candidate serves the 4-byte compare (:348) and stages the next
             // 5..12 bytes of the match (m1..m3, nmb of them valid) for the extension (:401-413).
             uint32_t m1 = 0, m2 = 0, m3 = 0, nmb = 0;
+            uint2 A = make_uint2(0u, 0u), B = A;
+            if (vold) {
+                const uint2* c8 = reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(src + old) & ~uintptr_t(7));
+                A = __ldg(c8);
+                B = __ldg(c8 + 1);   // (holds input bytes: old + 8 - c < n always, old < p <= n - 12)
+            }
+            if (DEFER && pM) {                                   // the previous window's sequences, under the reads just issued
+                if (!flush_batch(dst, cap, op, pM, pLit, ppk, ppk >> 8, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
+                pM = 0;
+            }
             if (vold) {
                 const uintptr_t ca = reinterpret_cast<uintptr_t>(src + old);
-                const uint2* c8 = reinterpret_cast<const uint2*>(ca & ~uintptr_t(7));
-                const uint2 A = __ldg(c8);
                 const uint32_t c = (uint32_t)(ca & 7);
-                // second half only if it holds input bytes (old + 8 - c < n always: old < p <= n - 12)
-                const uint2 B = __ldg(c8 + 1);
                 const uint32_t sh = (c & 3) * 8;
                 const bool hiw = c >= 4;
                 const uint32_t w0 = hiw ? A.y : A.x, w1 = hiw ? B.x : A.y, w2 = hiw ? B.y : B.x, w3 = hiw ? 0u : B.y;
@@ -759,7 +771,9 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 V |= 1u << lo;
                 if (mend + 1 >= lim) { finish = true; break; }           // :320
             }
-            if (M && !flush_batch(dst, cap, op, M, Lit, v, mseq, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
+            if (DEFER) {
+                if (M) { pM = M; pLit = Lit; ppk = (v & 0xFFu) | (mseq << 8); }
+            } else if (M && !flush_batch(dst, cap, op, M, Lit, v, mseq, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
             // ---------------- table after the window: last visited lane of every bucket, else unchanged ----------------
             {
                 const uint32_t vg = peers & V;
@@ -783,6 +797,10 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 const uint32_t mpos = search_later_windows<TableT>(src, table, lim, anchor + 1, base + 31 - anchor, lane, &mcand);
                 const bool found = mpos != 0xFFFFFFFFu;
                 if (!found) break;
+                if (DEFER && pM) {
+                    if (!flush_batch(dst, cap, op, pM, pLit, ppk, ppk >> 8, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
+                    pM = 0;
+                }
                 const uint32_t ml = extend_match(src, mpos, mcand, mlimit, lane);
                 if (!emit_sequence<TableT>(src, dst, cap, op, anchor, mpos - anchor, ml, mpos - mcand, false, 0, lane)) {
                     st = ST_OUTPUT_TOO_SMALL;
@@ -792,6 +810,7 @@ __device__ void compress_block_a1(const uint8_t* __restrict__ src, uint32_t n, u
                 e = anchor;
             }
         }
+        if (DEFER && pM && !flush_batch(dst, cap, op, pM, pLit, ppk, ppk >> 8, lane, lt)) { st = ST_OUTPUT_TOO_SMALL; return; }
     }
 
     // ---------------- last literals: compressAsLiterals :449-482 / finishCompression :484-519 ----------------
