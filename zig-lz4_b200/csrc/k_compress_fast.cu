@@ -909,6 +909,13 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
         set((const void*)k_compress_fast<uint32_t, false, 1, 13>, HASH_ENTRIES * 4);
         set((const void*)k_compress_fast<uint16_t, false, 7, 4>, 7 * HASH_ENTRIES * 2);
         set((const void*)k_compress_fast<uint32_t, false, 7, 2>, 7 * HASH_ENTRIES * 4);
+        // few blocks (at most one CTA per SM): leave the rest of the SM's memory to the L1, where the candidate reads of
+        // the seven windows in flight then find their blocks' recent history (4 MiB text blocks 127 -> 120 ms), and let
+        // the compiler have the registers it wants (no minimum of resident CTAs)
+        cudaFuncSetAttribute((const void*)k_compress_fast<uint32_t, false, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * HASH_ENTRIES * 4);
+        cudaFuncSetAttribute((const void*)k_compress_fast<uint32_t, false, 7, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute((const void*)k_compress_fast<uint16_t, false, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * HASH_ENTRIES * 2);
+        cudaFuncSetAttribute((const void*)k_compress_fast<uint16_t, false, 7, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
         set((const void*)k_compress_fast<uint16_t, true, 26, 1>, 26 * (HASH_ENTRIES * 2 + (int)RING_BYTES + (int)RING_SLOTS * 8));
         set((const void*)k_compress_fast<uint32_t, true, 13, 1>, 13 * (HASH_ENTRIES * 4 + (int)RING_BYTES + (int)RING_SLOTS * 8));
     });
@@ -940,7 +947,10 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
         uint32_t want = (nblocks + warps - 1) / warps;
         uint32_t maxg = (uint32_t)(num_sms * ctas_per_sm);
         uint32_t grid = want < maxg ? want : maxg;
-        if (small) k_compress_fast<uint16_t, false, 7, 4><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        const bool few = want <= (uint32_t)num_sms && t.k1_variant != 4;
+        if (small && few) k_compress_fast<uint16_t, false, 7, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        else if (small) k_compress_fast<uint16_t, false, 7, 4><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
+        else if (few) k_compress_fast<uint32_t, false, 7, 1><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
         else k_compress_fast<uint32_t, false, 7, 2><<<grid, warps * 32, smem, stream>>>(in, out, out_len, status, nblocks, accel, ticket);
     }
     count_launch();

@@ -35,7 +35,9 @@
 //   * matches that start in the external dictionary (:181-228) copy the dictionary tail first, then
 //     continue at dst[0..].
 #include "b2_common.cuh"
+#ifndef B2_EMU   // (B2_EMU: host build of the device code for the one-warp emulator, tools/warp_emu)
 #include "b2_kernels.h"
+#endif
 
 namespace b2 {
 
@@ -167,8 +169,13 @@ constexpr uint32_t PLAIN_SPAN = 18;
 // Length fields above this are left to the exact tier (keeps the 32-bit prefix sums exact).
 constexpr uint32_t FAST_LEN_MAX = 1u << 24;
 
+#ifdef B2_EMU
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+__device__ __forceinline__ void prefetch_l1(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
@@ -544,6 +551,7 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
     st = (int)r.y;
 }
 
+#ifndef B2_EMU
 template <int MIN_CTAS, int VARIANT>
 __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in, OutSet out, const uint32_t* __restrict__ hdr,
                                                            uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
@@ -696,5 +704,6 @@ cudaError_t launch_decoded_size(const BlockSet& in, const uint32_t* hdr, uint32_
     count_launch();
     return cudaGetLastError();
 }
+#endif  // !B2_EMU
 
 }  // namespace b2
