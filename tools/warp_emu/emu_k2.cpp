@@ -90,6 +90,32 @@ int main(int argc, char** argv) {
             }
         }
     }
+    // hand-built streams: every small offset (each period class of the overlapping-match copies) with short and long lengths,
+    // at varying output alignments
+    if (cls == 2) {
+        const uint32_t offs[] = {1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 24, 31, 32, 33, 48, 64, 65, 100, 255, 256, 1000};
+        const uint32_t lens[] = {4, 5, 15, 16, 17, 19, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 255, 256, 300, 511, 1024, 4000};
+        for (uint32_t off : offs)
+            for (uint32_t ml : lens) {
+                std::vector<uint8_t> st;
+                auto put_len = [&](uint32_t v) { while (v >= 255) { st.push_back(255); v -= 255; } st.push_back((uint8_t)v); };
+                uint32_t total = 0;
+                for (int rep = 0; rep < 3; rep++) {
+                    const uint32_t LL = off + (uint32_t)(rnd() % 7) + (rep == 0 ? 0 : 1);     // enough history, shifting alignment
+                    const uint32_t mlc = ml - 4;
+                    st.push_back((uint8_t)(((LL < 15 ? LL : 15) << 4) | (mlc < 15 ? mlc : 15)));
+                    if (LL >= 15) put_len(LL - 15);
+                    for (uint32_t i = 0; i < LL; i++) st.push_back((uint8_t)rnd());
+                    st.push_back((uint8_t)off); st.push_back((uint8_t)(off >> 8));
+                    if (mlc >= 15) put_len(mlc - 15);
+                    total += LL + ml;
+                }
+                st.push_back(0x50); for (int i = 0; i < 5; i++) st.push_back((uint8_t)rnd());   // last literals
+                total += 5;
+                check(st.data(), (uint32_t)st.size(), total, "hand-built");
+                check(st.data(), (uint32_t)st.size(), total + 17, "hand-built roomy");
+            }
+    }
     printf("K2 class %d: %llu decodes checked, %llu failed\n", cls, (unsigned long long)g_checked, (unsigned long long)g_failed);
     return g_failed ? 1 : 0;
 }

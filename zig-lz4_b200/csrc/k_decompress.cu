@@ -67,13 +67,87 @@ __device__ __forceinline__ bool read_len_ext(const uint8_t* __restrict__ src, ui
     }
 }
 
-// Forward-overlap-safe copy of `ml` bytes to d from s = d - offset (both inside the output buffer).
-__device__ __forceinline__ void match_copy(uint8_t* d, const uint8_t* s, uint32_t offset, uint32_t ml, uint32_t lane) {
-    if (offset >= ml) {
-        warp_copy<false>(d, s, ml, lane);
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, uint32_t i) {   // byte i (0..15) of a 16-byte vector
+    const uint32_t w = i < 8 ? (i < 4 ? v.x : v.y) : (i < 12 ? v.z : v.w);
+    return (w >> ((i & 3) * 8)) & 0xFFu;
+}
+
+// Overlapping match whose period divides 16 (byte / u16 / u32 / u64 runs, 16-byte patterns): the output is one 16-byte
+// vector repeated, so it is read once and written with aligned 16-byte stores — no read-back of what was just written
+// (the doubling rounds below are a store -> load round trip through L2 each: eight of them for a 255-byte run).
+__device__ __forceinline__ void match_fill_pow2(uint8_t* d, const uint8_t* s, uint32_t offset, uint32_t ml, uint32_t lane) {
+    const uint32_t bo = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 15);
+    const uint4* a16 = reinterpret_cast<const uint4*>(s - bo);
+    const uint4 A = a16[0];
+    const uint4 B = bo + offset > 16 ? a16[1] : A;            // only if the pattern reaches into it (then it holds pattern bytes)
+    const uint4 X = extract16(A, B, bo);                       // s[0..15]; only the first `offset` bytes are pattern
+    uint4 P;                                                   // P[b] = s[b mod offset]
+    if (offset == 16) P = X;
+    else if (offset == 8) P = make_uint4(X.x, X.y, X.x, X.y);
+    else {
+        const uint32_t w = offset == 4 ? X.x : (offset == 2 ? (X.x & 0xFFFFu) * 0x00010001u : (X.x & 0xFFu) * 0x01010101u);
+        P = make_uint4(w, w, w, w);
+    }
+    const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+    if (ml <= head) { if (lane < ml) d[lane] = (uint8_t)byte_of(P, lane); return; }
+    if (lane < head) d[lane] = (uint8_t)byte_of(P, lane);
+    const uint4 V = extract16(P, P, head & (offset - 1));       // the vector at every 16-aligned output position
+    const uint32_t rest = ml - head, nvec = rest >> 4, tail = rest & 15;
+    uint4* d16 = reinterpret_cast<uint4*>(d + head);
+    for (uint32_t i = lane; i < nvec; i += 32) d16[i] = V;
+    if (lane < tail) d[head + (nvec << 4) + lane] = (uint8_t)byte_of(V, lane);
+}
+
+// Self-overlapping match (offset < ml), every method.  Used at ONE site, the serial front end's long matches (runs and
+// repeated patterns are what that front end is chosen for).  The decoder is 9700 instructions: with this code inlined at
+// all four match-copy sites the mixed workload waited 3.4 instead of 1.2 cycles per issue for instructions (blocks of
+// different kinds are decoded side by side) and lost more than the runs gained; as an out-of-line function the call
+// cost the chunked decoder's hot loop its registers (text 4.45 -> 4.73 ms per GiB).  The other sites keep the plain
+// doubling copy.
+__device__ __forceinline__ void match_copy_overlap(uint8_t* d, const uint8_t* s, uint32_t offset, uint32_t ml, uint32_t lane) {
+    if (offset <= 16 && (offset & (offset - 1)) == 0) {
+        match_fill_pow2(d, s, offset, ml, lane);
+        return;
+    }
+    if (offset >= 16 && ml >= 2 * offset + 64) {
+        // One period first; then [s, s + 2 * offset) is valid and periodic, and every 16-byte vector of the rest can be
+        // read from inside it at its own phase: two rounds whatever the length (doubling: log2(ml / offset) + 1).
+        warp_copy<false>(d, s, offset, lane);
+        __syncwarp();
+        uint8_t* d2 = d + offset;
+        const uint32_t rest0 = ml - offset;
+        const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d2) & 15)) & 15);
+        if (lane < head) d2[lane] = s[lane];                    // (head < 16 <= offset)
+        const uint32_t rest = rest0 - head, nvec = rest >> 4, tail = rest & 15;
+        uint4* d16 = reinterpret_cast<uint4*>(d2 + head);
+        for (uint32_t i = lane; i < nvec; i += 32) {
+            const uint8_t* ps = s + (head + 16 * i) % offset;
+            const uint32_t bo = (uint32_t)(reinterpret_cast<uintptr_t>(ps) & 15);
+            const uint4* a16 = reinterpret_cast<const uint4*>(ps - bo);
+            const uint4 A = a16[0];
+            const uint4 B = bo ? a16[1] : A;
+            d16[i] = extract16(A, B, bo);
+        }
+        if (lane < tail) d2[head + (nvec << 4) + lane] = s[(head + (nvec << 4) + lane) % offset];
+        __syncwarp();
         return;
     }
     uint32_t copied = 0, avail = offset;
+    while (copied < ml) {
+        uint32_t chunk = ml - copied < avail ? ml - copied : avail;
+        warp_copy<false>(d + copied, s, chunk, lane);
+        __syncwarp();
+        copied += chunk;
+        avail += chunk;
+    }
+}
+
+// Forward-overlap-safe copy of `ml` bytes to d from s = d - offset (both inside the output buffer).
+template <bool FULL_METHODS = false>
+__device__ __forceinline__ void match_copy(uint8_t* d, const uint8_t* s, uint32_t offset, uint32_t ml, uint32_t lane) {
+    if (offset >= ml) { warp_copy<false>(d, s, ml, lane); return; }
+    if (FULL_METHODS) { match_copy_overlap(d, s, offset, ml, lane); return; }
+    uint32_t copied = 0, avail = offset;     // period doubling
     while (copied < ml) {
         uint32_t chunk = ml - copied < avail ? ml - copied : avail;
         warp_copy<false>(d + copied, s, chunk, lane);
@@ -201,6 +275,7 @@ __device__ __forceinline__ uint32_t count_le(uint32_t sorted_v, uint32_t x) {
 // length myML), in stream order; output continues at op.  Returns false — nothing this batch wrote matters — when a
 // sequence needs the exact tier's judgement: offset 0 (:154), a match reaching before dst (:181 / :231), output
 // overflow (:137 / :174).
+template <bool TWO_ROUND>   // true (serial front end: runs, repeated patterns): overlapping long matches by match_copy_overlap
 __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, uint8_t* dst, uint32_t cap, uint32_t lane,
                                              uint32_t k, uint32_t myLit, uint32_t myLL, uint32_t myML, uint32_t& op) {
     const bool valid = lane < k;
@@ -339,7 +414,7 @@ __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, ui
                 const int j = __ffs(gm) - 1;
                 gm &= gm - 1;
                 const uint32_t jms = __shfl_sync(FULL, ms, j), joff = __shfl_sync(FULL, off, j);
-                match_copy(dst + jms, dst + jms - joff, joff, __shfl_sync(FULL, myML, j), lane);
+                match_copy<TWO_ROUND>(dst + jms, dst + jms - joff, joff, __shfl_sync(FULL, myML, j), lane);
             }
             if (go) pending = false;
             __syncwarp();
@@ -387,7 +462,7 @@ __device__ void decode_block_fast_v1(const uint8_t* __restrict__ src, uint32_t n
                 }
             }
             if (k == 0) break;
-            if (!expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) { ip = ip0; break; }
+            if (!expand_batch<true>(src, dst, cap, lane, k, myLit, myLL, myML, op)) { ip = ip0; break; }
             if (stop) break;
         }
     }
@@ -488,20 +563,21 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
             // ---------------- the serial part: up to 32 dependent shared-memory reads, in groups of 8 ----------------
             uint32_t p2 = 2 * (uint32_t)((int32_t)ip - cb);          // twice the chunk position = byte offset into delta[]
             uint32_t steps = 32;
+            uint32_t myp2 = 0;                                       // where the walk stood at step `lane` (kept in a register: the
+                                                                     // kernel is bound by the load/store pipe, not by the ALUs)
 #pragma unroll
             for (int g8 = 0; g8 < 4; g8++) {
                 uint32_t d = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    ws->pos[g8 * 8 + k] = (uint16_t)p2;
+                    if (lane == (uint32_t)(g8 * 8 + k)) myp2 = p2;
                     d = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(ws->delta) + p2);
                     p2 += d;
                 }
                 if (g8 < 3 && d == 0) { steps = 8 * (g8 + 1); break; }   // the walk stands still: nothing more in this chunk
             }
-            ws->pos[32] = (uint16_t)p2;
             // ---------------- every lane decodes its own token from the staged bytes and checks the speculation ----------------
-            const uint32_t mp = ws->pos[lane] >> 1;                  // (lanes >= steps read a stale but in-range position)
+            const uint32_t mp = myp2 >> 1;                           // (lanes >= steps: position 0, in range, never live)
             const bool live = lane < steps && ws->delta[mp] != 0;    // halting (chunk end / exact-tier zone) is absorbing: a prefix of lanes
             uint32_t myLit = 0, myLL = 0, myML = 0;
             bool bad = false;
@@ -527,12 +603,13 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
             uint32_t k = (uint32_t)__popc(lm);
             const bool cut = bm != 0;                                // a token needs the exact tier: the batch ends before it
             if (cut) k = (uint32_t)__ffs(bm) - 1;
-            const uint32_t ipn = (uint32_t)(cb + (int32_t)(ws->pos[k] >> 1));
+            const uint32_t pk = __shfl_sync(FULL, myp2, k);          // (k == 32: where the walk stands after its last step)
+            const uint32_t ipn = (uint32_t)(cb + (int32_t)((k == 32 ? p2 : pk) >> 1));
             if (lane >= k) { myLL = 0; myML = 0; }
             // the next chunk's lines into L1 while this batch is expanded (its staging then costs an L1 hit, not an L2 round trip)
             if (lane < 3 && ipn + lane * 128 < isafe) prefetch_l1(src + ipn + lane * 128);
             __syncwarp();                                            // staged bytes are dead from here (next chunk overwrites them)
-            if (k != 0 && !expand_batch(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
+            if (k != 0 && !expand_batch<false>(src, dst, cap, lane, k, myLit, myLL, myML, op)) break;   // ip still at the batch start
             ip = ipn;
             staged_ok = (int32_t)ip - cb <= (int32_t)CHUNK - 56;
             if (cut) {
@@ -678,7 +755,7 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     // CTAs of 4 warps per SM: 8 (64 registers, no spills) by default; b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
     // occupancy experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end (10 per SM).
     const int occ_t = tune().k2_occ, variant = tune().k2_variant == 1 ? 1 : 2;
-    const int occ = (occ_t == 8 || occ_t == 9 || occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
+    const int occ = (occ_t == 6 || occ_t == 7 || occ_t == 8 || occ_t == 9 || occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
@@ -687,6 +764,7 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
         if (occ == 12) B2_K2_LAUNCH(12, 1); else if (occ == 8) B2_K2_LAUNCH(8, 1); else B2_K2_LAUNCH(10, 1);
     } else {
         if (occ == 12) B2_K2_LAUNCH(12, 2); else if (occ == 10) B2_K2_LAUNCH(10, 2); else if (occ == 9) B2_K2_LAUNCH(9, 2);
+        else if (occ == 7) B2_K2_LAUNCH(7, 2); else if (occ == 6) B2_K2_LAUNCH(6, 2);
         else B2_K2_LAUNCH(8, 2);
     }
 #undef B2_K2_LAUNCH
