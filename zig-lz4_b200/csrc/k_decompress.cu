@@ -210,7 +210,7 @@ __device__ __forceinline__ int exact_step(const uint8_t* __restrict__ src, uint3
     } else {
         if (WRITE) {
             __syncwarp();  // literals written by other lanes must be visible
-            match_copy(dst + op, dst + op - offset, offset, ML, lane);  // :232-246
+            match_copy<true>(dst + op, dst + op - offset, offset, ML, lane);  // :232-246
             __syncwarp();
         }
         op += ML;
@@ -504,7 +504,6 @@ constexpr uint32_t DELTA_SLOTS = 544;  // the walk may stand on any position < C
 struct __align__(16) WarpStage {
     uint8_t bytes[CHUNK + CHUNK_MARGIN];
     uint16_t delta[DELTA_SLOTS];
-    uint16_t pos[40];                  // [32] = where the walk stands after its last step
 };
 
 // Token lengths of four positions at once, SPECULATIVELY: the bytes of `x` are candidate tokens, the bytes of `xs` the
@@ -663,14 +662,21 @@ __global__ void __launch_bounds__(K2_THREADS, MIN_CTAS) k_decompress(BlockSet in
             if (n > cap) st = ST_RAW_NO_ROOM;
             else { warp_copy<true>(dst, src, n, lane); olen = n; }
         } else if (VARIANT == 1) {
-            decode_block_fast_v1(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, 0, 0, olen, st);
-        } else if (has_dict || (uint64_t)n * 6 < cap) {
+            decode_block_fast_v1(src, n, dst, cap, dict, dict_len, (has_dict & 1) != 0, lane, 0, 0, olen, st);
+        } else if ((has_dict & 1) || (uint64_t)n * 6 < cap) {
             // Streams that shrink their block more than 6 x are runs and long matches: every few tokens one with a
-            // 255-extended length, which the chunked front end's speculation has to cut the batch at.  The serial walk
-            // handles those in place and keeps 32 sequences per batch (redundant class: 1.7 against 2.9 ms per GiB).
-            // Dictionary decodes (small records) go the same way: the chunked tier leaves every match that reaches
-            // before the block to the exact tier anyway.
-            const uint2 r = fast_v1_ool(src, n, dst, cap, dict, dict_len, has_dict != 0, lane, 0, 0);
+            // 255-extended length, which the chunked front end's speculation has to cut the batch at.  They go to the
+            // EXACT tier, one sequence at a time, every copy warp-wide (runs and repeated patterns without read-back,
+            // match_copy_overlap): nearly every sequence of such a stream is long, so batching 32 of them gains nothing,
+            // and the exact tier's loop is compact — the serial front end (the round-1 decoder) is as fast on such
+            // streams alone (1.48 ms per GiB both) but walks so much code per sequence that it waits 2.6 cycles per
+            // issue for instructions and, decoded side by side with other kinds of blocks, takes their instruction cache
+            // with it: mixed workload 3.10 -> 2.85 ms per GiB.  Dictionary decodes (small records) keep the serial front
+            // end: the chunked tier leaves every match that reaches before the block to the exact tier anyway.
+            // (has_dict: bit 0 = dictionary, bit 1 = exact tier for compressible streams; b2lz4_debug_tune("spare2", 1)
+            // restores the serial front end for A/B runs.)
+            const uint2 r = ((has_dict & 3) == 2) ? finish_exact_ool(src, n, dst, cap, dict, dict_len, (has_dict & 1) != 0, lane, 0, 0)
+                                           : fast_v1_ool(src, n, dst, cap, dict, dict_len, (has_dict & 1) != 0, lane, 0, 0);
             olen = r.x;
             st = (int)r.y;
         } else {
@@ -722,6 +728,30 @@ __global__ void __launch_bounds__(1024) k_order_heavy_first(const uint32_t* __re
     }
 }
 
+// Decode order by stored size, largest first, in buckets of 1 KiB (stored blocks last): a counting sort in one CTA.
+// Blocks of one kind compress to similar sizes, so the warps resident at any time mostly run the same paths of this
+// 9700-instruction kernel (the instruction caches hold 2000), and the expensive blocks still go first.
+__global__ void __launch_bounds__(1024) k_order_by_size(const uint32_t* __restrict__ hdr, uint32_t nblocks, uint32_t block_size,
+                                                        uint32_t* __restrict__ order) {
+    constexpr uint32_t NB = 258;                 // bucket 0: largest ... 256: smallest, 257: stored
+    __shared__ uint32_t cnt[NB];
+    __shared__ uint32_t base[NB];
+    const uint32_t tid = threadIdx.x;
+    auto bucket = [&](uint32_t i) -> uint32_t {
+        const uint32_t h = hdr[i];
+        if (h & 0x80000000u) return 257u;
+        const uint32_t kib = (h & 0x7FFFFFFFu) * 256u / (block_size ? block_size : 1u);   // 0..256 relative to the block size
+        return 256u - (kib > 256u ? 256u : kib);
+    };
+    for (uint32_t b = tid; b < NB; b += 1024) cnt[b] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < nblocks; i += 1024) atomicAdd(&cnt[bucket(i)], 1u);
+    __syncthreads();
+    if (tid == 0) { uint32_t run = 0; for (uint32_t b = 0; b < NB; b++) { base[b] = run; run += cnt[b]; } }
+    __syncthreads();
+    for (uint32_t i = tid; i < nblocks; i += 1024) order[atomicAdd(&base[bucket(i)], 1u)] = i;
+}
+
 // Natural decoded size of every block (unbounded output, nothing written).
 __global__ void __launch_bounds__(K2_THREADS) k_decoded_size(BlockSet in, const uint32_t* __restrict__ hdr,
                                                              uint32_t* __restrict__ out_len,
@@ -747,7 +777,8 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     if (e != cudaSuccess) return e;
     const uint32_t* order = nullptr;
     if (order_scratch && hdr && block_size && nblocks > (uint32_t)num_sms * 8 && tune().spare[0] == 0) {
-        k_order_heavy_first<<<1, 1024, 0, stream>>>(hdr, nblocks, block_size, order_scratch);
+        if (tune().spare[1] == 1) k_order_heavy_first<<<1, 1024, 0, stream>>>(hdr, nblocks, block_size, order_scratch);
+        else k_order_by_size<<<1, 1024, 0, stream>>>(hdr, nblocks, block_size, order_scratch);
         count_launch();
         order = order_scratch;
     }
@@ -759,7 +790,7 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
-                                                                              dict_len, dict != nullptr ? 1 : 0, ticket, order)
+                                                                              dict_len, (dict != nullptr ? 1 : 0) | (tune().spare[2] ? 0 : 2), ticket, order)
     if (variant == 1) {
         if (occ == 12) B2_K2_LAUNCH(12, 1); else if (occ == 8) B2_K2_LAUNCH(8, 1); else B2_K2_LAUNCH(10, 1);
     } else {
