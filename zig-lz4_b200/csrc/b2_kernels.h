@@ -30,6 +30,12 @@ cudaError_t launch_compress_fast(const BlockSet& in, const OutSet& out, uint32_t
                                  uint32_t nblocks, uint32_t max_len, uint32_t accel, uint32_t* ticket, int num_sms,
                                  cudaStream_t stream);
 
+// the same over regular block sets with the blocks taken expensive-first (estimate pass + order: k_compress_fast.cu);
+// scratch: order_scratch_bytes(nblocks) of device memory
+size_t order_scratch_bytes(uint32_t nblocks);
+cudaError_t launch_compress_fast_ordered(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status, uint32_t nblocks,
+                                         uint32_t max_len, uint32_t* ticket, int num_sms, void* scratch, cudaStream_t stream);
+
 // fast compressor with a shared dictionary (k_compress_dict.cu); primed: 4096 u32 of device scratch
 cudaError_t launch_compress_fast_dict(const BlockSet& in, const OutSet& out, uint32_t* out_len, int32_t* status,
                                       uint32_t nblocks, const uint8_t* dict, uint64_t dict_len, uint32_t* primed,
