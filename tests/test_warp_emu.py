@@ -1,7 +1,9 @@
 """K1 / K2 device code executed on the host (tools/warp_emu: every lane a coroutine, every warp collective a rendezvous)
 and compared with the oracle: the kernels' LOGIC — window walk, static match chain, batched emit, forward word ring,
 chunked / serial decode front ends, exact tier, error kinds — is checked here, where there is no GPU.  The GPU suite
-checks the compiled kernels; this one makes a logic regression visible in the CPU tier already.
+checks the compiled kernels; this one makes a logic regression visible in the CPU tier already.  Inputs and outputs sit
+between inaccessible pages (emu::Guarded): a read or write outside the 16-byte granules that hold the buffers' own bytes
+— which no tool reports on the GPU box, compute-sanitizer being closed there — is a crash here.
 Reference semantics: /root/reference/src/lz4.zig:292-447 (compressFast), :89-259 (decompressGeneric)."""
 import os
 import subprocess

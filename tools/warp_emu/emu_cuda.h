@@ -33,7 +33,37 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 
+#include <sys/mman.h>
+#include <unistd.h>
+
 namespace emu {
+
+// A buffer of n bytes between two inaccessible pages: `at_end` puts its last byte right before the guard page behind it
+// (any read or write past the end faults), otherwise its first byte sits `lead` bytes after the guard page in front (any
+// access below the 16-byte granule that holds the first byte faults, for lead < 16).  The kernels promise to touch only
+// aligned granules that hold at least one valid byte; on the GPU nothing would report a violation, here it is a SIGSEGV.
+struct Guarded {
+    uint8_t* map = nullptr; size_t map_len = 0; uint8_t* p = nullptr;
+    Guarded(size_t n, bool at_end, size_t lead = 0) {
+        const size_t pg = (size_t)sysconf(_SC_PAGESIZE);
+        const size_t body = (n + lead + pg - 1) / pg * pg + pg;      // one spare page so that both placements fit
+        map_len = body + 2 * pg;
+        map = (uint8_t*)mmap(nullptr, map_len, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (map == MAP_FAILED) { perror("mmap"); abort(); }
+        if (mprotect(map + pg, body, PROT_READ | PROT_WRITE) != 0) { perror("mprotect"); abort(); }
+        if (at_end) {
+            // the accessible part must END at the byte after the buffer: shrink it so the guard page follows directly
+            const size_t used = (n + pg - 1) / pg * pg;
+            if (mprotect(map + pg + used, body - used, PROT_NONE) != 0) { perror("mprotect"); abort(); }
+            p = map + pg + used - n;
+        } else {
+            p = map + pg + lead;
+        }
+    }
+    ~Guarded() { if (map) munmap(map, map_len); }
+    Guarded(const Guarded&) = delete;
+    Guarded& operator=(const Guarded&) = delete;
+};
 
 constexpr int W = 32;
 struct Warp {

@@ -39,8 +39,13 @@ static void check(const uint8_t* comp, uint32_t clen, uint32_t cap, const char* 
         uint32_t olen = 0;
         // the stream sits at the very end of its allocation: a read past it would fault under a checker, and damaged
         // streams exercise the bounds logic
-        std::vector<uint8_t> tight(comp, comp + clen);
-        const int st = run_decode(tier, tight.data(), clen, got.data(), cap, nullptr, 0, olen);
+        static uint64_t flip = 0;
+        const bool at_end = (flip++ & 1) == 0;
+        emu::Guarded gs(clen ? clen : 1, at_end, (size_t)(flip * 7 % 16));
+        memcpy(gs.p, comp, clen);
+        emu::Guarded gd(cap ? cap : 1, (flip & 2) != 0, (size_t)(flip * 3 % 16));   // output: guard behind its end or in front of its start
+        const int st = run_decode(tier, gs.p, clen, gd.p, cap, nullptr, 0, olen);
+        memcpy(got.data(), gd.p, cap);
         g_checked++;
         bool ok = st == wst;
         if (ok && st == 0) ok = olen == wlen && memcmp(got.data(), want.data(), wlen) == 0;
