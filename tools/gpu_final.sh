@@ -21,7 +21,7 @@ PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O.launches.csv \
    python bench.py --steps 2 --warmup 1 --no-extra --no-e2e --no-cpu-baseline > $O.ncu_launches.log 2>&1
 # full capture of the two codec kernels on the bench workload
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_compress_fast|k_decompress" -c 2 -o $O.k1k2 -f \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_compress_fast|k_decompress" -c 3 -o $O.k1k2 -f \
    python bench.py --steps 1 --warmup 1 --no-extra --no-e2e --no-cpu-baseline > $O.ncu_full.log 2>&1
 ncu -i $O.k1k2.ncu-rep --page raw --csv > $O.k1k2_raw.csv 2>> $O.ncu_full.log
 ncu -i $O.k1k2.ncu-rep --page source --csv --print-source cuda,sass -k regex:k_compress_fast > $O.k1_source.csv 2>> $O.ncu_full.log

@@ -24,11 +24,15 @@ def main():
     def val(r, name):
         return float(r[col[name]]) * UNIT.get(units[col[name]], 1)
 
+    # the longest launch of each kernel: K1 also runs a short estimate pass (first KiB of every block) before the real one
+    best = {}
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         key = "k_compress_fast" if "k_compress_fast" in name else ("k_decompress" if "k_decompress" in name else None)
-        if not key or key in out:
-            continue
+        if key and (key not in best or val(r, "gpu__time_duration.sum") > val(best[key], "gpu__time_duration.sum")):
+            best[key] = r
+    for key, r in best.items():
+        name = r[col["Kernel Name"]]
         out[key] = {"traffic_bytes": int(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")),
                     "dram_read_bytes": int(val(r, "dram__bytes_read.sum")), "dram_write_bytes": int(val(r, "dram__bytes_write.sum")),
                     "ncu_duration_ms": round(val(r, "gpu__time_duration.sum") * (1e-6 if units[col["gpu__time_duration.sum"]] == "ns" else 1e-3 if units[col["gpu__time_duration.sum"]] == "us" else 1), 3),

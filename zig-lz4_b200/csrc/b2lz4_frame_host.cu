@@ -238,6 +238,12 @@ static int compress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, 
 
 // Returns 1 if the frame was decoded (or a CUDA error is reported through *rc_out), 0 if the caller must take
 // the one-shot path (anything unusual).
+//
+// The block index is the header chain read straight from the caller's (host) frame, src/lz4f.zig:563-591 — 16 384
+// dependent reads 36 KB apart for a 1 GiB frame of 64 KiB blocks: 1.85 ms of cache and TLB misses on the bench box
+// (tools/exp/host_walk_bench.cu), 7 % of the whole call, during which neither the link nor the GPU did anything.  Long
+// frames therefore start early: the chain is walked for the first two (ramp-sized) chunks only, those are enqueued, and
+// the rest of the chain is walked while they upload and decode.
 static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out,
                                       int* rc_out) {
     *rc_out = B2LZ4_OK;
@@ -247,55 +253,98 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
     const bool page_src = b2::HostMover::pageable(src), page_dst = b2::HostMover::pageable(dst);
     const bool bc = info.block_checksum == 1, cc = info.content_checksum == 1;
     const size_t tr = bc ? 4 : 0;
-    // block index: the header chain read straight from the caller's (host) frame, src/lz4f.zig:563-591
+    if (b2::tune().no_pipeline) return 0;
+    bool forced;
+    const size_t chunk_blocks = pipe_blocks_for(bs, &forced);
+    if (!forced && chunk_blocks < 1024) return 0;
+
+    // ---- the header chain, walked on demand
     std::vector<uint64_t> off;
     std::vector<uint32_t> hdr;
     off.reserve(n / 1024 + 16); hdr.reserve(n / 1024 + 16);
     size_t p = hsize;
-    bool end_mark = false;
-    while (p < n) {
-        if (p + 4 > n) return 0;
-        const uint32_t h = rd32(src + p);
-        p += 4;
-        if (h == 0) { end_mark = true; break; }
-        const size_t sz = h & 0x7FFFFFFFu;
-        if (p + sz + tr > n || sz > bs) return 0;
-        off.push_back(p); hdr.push_back(h);
-        p += sz + tr;
+    bool end_mark = false, malformed = false;
+    auto walk_until = [&](size_t want_blocks) {          // stops at the end mark, at anything unusual, or with want_blocks known
+        while (!end_mark && !malformed && off.size() < want_blocks) {
+            if (p >= n || p + 4 > n) { malformed = true; break; }       // ran off the frame without an end mark
+            const uint32_t h = rd32(src + p);
+            p += 4;
+            if (h == 0) { end_mark = true; break; }
+            const size_t sz = h & 0x7FFFFFFFu;
+            if (p + sz + tr > n || sz > bs) { malformed = true; break; }
+            off.push_back(p); hdr.push_back(h);
+            p += sz + tr;
+        }
+    };
+    const size_t q = std::max<size_t>(1, chunk_blocks / 4), hh = std::max<size_t>(1, chunk_blocks / 2);
+    walk_until(q + hh);
+    if (malformed) return 0;
+    // early start only when the frame surely has the >= 4 chunks the ramped plan needs (judged by the records seen so far)
+    bool early = false;
+    if (!end_mark && off.size() == q + hh) {
+        const double avg = (double)(p - hsize) / (double)(q + hh);
+        early = (double)(n - hsize) / avg >= 4.4 * (double)chunk_blocks && cap / bs + 2 < 0x7FFFFFFFull;
     }
-    if (!end_mark || off.empty() || off.size() > 0x7FFFFFFFull) return 0;
-    if (cc && p + 4 > n) return 0;
-    const size_t nb = off.size();
-    if (cap < (nb - 1) * bs + 1) return 0;                       // optimistic layout needs room for every block start
-    size_t chunk_blocks;
-    if (!pipeline_applies(nb * bs, bs, &chunk_blocks)) return 0;
-    const std::vector<size_t> cfirst = chunk_plan(nb, chunk_blocks, true, true);   // first block of each chunk (+ sentinel)
-    const size_t nchunks = cfirst.size() - 1;
-    size_t max_in = 0, max_blocks = 0;
-    for (size_t k = 0; k < nchunks; k++) {
-        const size_t i0 = cfirst[k], i1 = cfirst[k + 1];
-        max_in = std::max(max_in, (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - (off[i0] - 4)));
-        max_blocks = std::max(max_blocks, i1 - i0);
+    if (!early) {
+        walk_until(SIZE_MAX);
+        if (malformed || !end_mark) return 0;
     }
+    auto frame_ok = [&]() {                              // the checks that need the whole chain
+        if (malformed || !end_mark || off.empty() || off.size() > 0x7FFFFFFFull) return false;
+        if (cc && p + 4 > n) return false;
+        if (cap < (off.size() - 1) * bs + 1) return false;            // optimistic layout needs room for every block start
+        return off.size() * bs > 2 * chunk_blocks * bs;                // (pipeline_applies)
+    };
+    if (!early && !frame_ok()) return 0;
+
+    // ---- chunk plan: first block of each chunk (+ sentinel).  With an early start only its head is known yet.
+    std::vector<size_t> cfirst;
+    if (early) { cfirst = {0, q, q + hh}; }
+    else cfirst = chunk_plan(off.size(), chunk_blocks, true, true);
+    size_t nchunks = early ? SIZE_MAX : cfirst.size() - 1;          // SIZE_MAX: not known yet
+    // ---- buffers: exact sizes when the whole chain is known, bounds otherwise
+    const size_t nb_bound = early ? cap / bs + 2 : off.size();
+    size_t max_in = 0;
+    if (early) max_in = chunk_blocks * (4 + bs + tr);
+    else
+        for (size_t k = 0; k + 1 < cfirst.size(); k++) {
+            const size_t i0 = cfirst[k], i1 = cfirst[k + 1];
+            max_in = std::max(max_in, (size_t)(off[i1 - 1] + (hdr[i1 - 1] & 0x7FFFFFFFu) + tr - (off[i0] - 4)));
+        }
     auto fail = [&](cudaError_t e, const char* what) { set_cuda_error(e, what); *rc_out = B2LZ4_ERR_CUDA; pipe_drain(c); return 1; };
 #define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(_e, #expr); } while (0)
     for (int b = 0; b < PIPE_DEPTH; b++) {
         PIPE_CUDA(c->stage_in[b].ensure(max_in + 32));
-        PIPE_CUDA(c->stage_out[b].ensure(max_blocks * bs + 16));
+        PIPE_CUDA(c->stage_out[b].ensure(chunk_blocks * bs + 16));
     }
-    PIPE_CUDA(c->walk_off.ensure(nb * 8));
-    PIPE_CUDA(c->walk_hdr.ensure(nb * 4));
-    PIPE_CUDA(c->out_len.ensure(nb * 4 + 4));
-    PIPE_CUDA(c->status.ensure(nb * 4 + 4));
-    PIPE_CUDA(c->sums.ensure(nb * 4 + 4));
-    // per-chunk relative offsets (each chunk's bytes land at the start of its staging buffer)
-    std::vector<uint64_t> rel(nb);
-    for (size_t k = 0; k < nchunks; k++) {
-        const uint64_t lo = off[cfirst[k]] - 4;
-        for (size_t i = cfirst[k]; i < cfirst[k + 1]; i++) rel[i] = off[i] - lo;
-    }
-    PIPE_CUDA(cudaMemcpyAsync(c->walk_off.p, rel.data(), nb * 8, cudaMemcpyHostToDevice, c->copy_in));
-    PIPE_CUDA(cudaMemcpyAsync(c->walk_hdr.p, hdr.data(), nb * 4, cudaMemcpyHostToDevice, c->copy_in));
+    PIPE_CUDA(c->walk_off.ensure(nb_bound * 8));
+    PIPE_CUDA(c->walk_hdr.ensure(nb_bound * 4));
+    PIPE_CUDA(c->out_len.ensure(nb_bound * 4 + 4));
+    PIPE_CUDA(c->status.ensure(nb_bound * 4 + 4));
+    PIPE_CUDA(c->sums.ensure(nb_bound * 4 + 4));
+    // per-chunk relative offsets (each chunk's bytes land at the start of its staging buffer), uploaded as far as known
+    std::vector<uint64_t> rel;
+    size_t rel_done = 0, chunks_rel = 0;                             // blocks / chunks whose index entries are on the device
+    auto upload_index = [&]() -> cudaError_t {
+        const size_t known_chunks = cfirst.size() - 1;
+        rel.resize(cfirst[known_chunks]);
+        for (size_t k = chunks_rel; k < known_chunks; k++) {
+            const uint64_t lo = off[cfirst[k]] - 4;
+            for (size_t i = cfirst[k]; i < cfirst[k + 1]; i++) rel[i] = off[i] - lo;
+        }
+        const size_t upto = cfirst[known_chunks];
+        cudaError_t e = cudaSuccess;
+        if (upto > rel_done) {
+            e = cudaMemcpyAsync(c->walk_off.as<uint64_t>() + rel_done, rel.data() + rel_done, (upto - rel_done) * 8,
+                                cudaMemcpyHostToDevice, c->copy_in);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(c->walk_hdr.as<uint32_t>() + rel_done, hdr.data() + rel_done, (upto - rel_done) * 4,
+                                    cudaMemcpyHostToDevice, c->copy_in);
+        }
+        rel_done = upto; chunks_rel = known_chunks;
+        return e;
+    };
+    PIPE_CUDA(upload_index());
     cudaEvent_t* ev_up = &c->ev_pipe[0];
     cudaEvent_t* ev_done = &c->ev_pipe[3];
     cudaEvent_t* ev_down = &c->ev_pipe[6];
@@ -304,7 +353,21 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
     bool unusual = false;
     size_t total = 0;
     const size_t lead = PIPE_DEPTH - 1;
-    for (size_t k = 0; k < nchunks + lead && !unusual; k++) {
+    for (size_t k = 0; (nchunks == SIZE_MAX || k < nchunks + lead) && !unusual; k++) {
+        if (nchunks == SIZE_MAX && k + 1 >= cfirst.size()) {
+            // the chunks known so far are enqueued: walk the rest of the chain under their uploads, finish the plan
+            walk_until(SIZE_MAX);
+            if (!frame_ok() || off.size() > nb_bound) { unusual = true; break; }
+            const size_t nb = off.size();
+            size_t i = q + hh;
+            const bool tl = nb >= 4 * chunk_blocks && nb > i + q + hh;        // ramp down at the end, as chunk_plan does
+            const size_t tail = tl ? q + hh : 0;
+            while (i + tail < nb) { cfirst.push_back(std::min(i + chunk_blocks, nb - tail)); i = cfirst.back(); }
+            if (tl) { cfirst.push_back(nb - q); cfirst.push_back(nb); }
+            if (cfirst.back() != nb) cfirst.push_back(nb);
+            nchunks = cfirst.size() - 1;
+            PIPE_CUDA(upload_index());
+        }
         if (k < nchunks) {
             const int b = (int)(k % PIPE_DEPTH);
             const b2_ws_ref w = c->ws(b);
@@ -328,7 +391,8 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
             const uint8_t* d_in = c->stage_in[b].as<uint8_t>();
             if (bc) PIPE_CUDA(launch_xxh32_ranges(d_in, d_off, d_hdr, d_sum, (uint32_t)cnt, s));
             BlockSet in; in.base = d_in; in.off = d_off; in.len = d_hdr; in.stride = 0; in.total = 0; in.len_mask = 0x7FFFFFFFu;
-            const uint64_t out_room = std::min<uint64_t>((uint64_t)cnt * bs, cap - (uint64_t)i0 * bs);
+            const uint64_t room = cap > (uint64_t)i0 * bs ? cap - (uint64_t)i0 * bs : 0;
+            const uint64_t out_room = std::min<uint64_t>((uint64_t)cnt * bs, room);
             OutSet o; o.base = c->stage_out[b].as<uint8_t>(); o.off = nullptr; o.cap = nullptr; o.stride = bs; o.total = out_room;
             o.slot_cap = (uint32_t)bs;
             PIPE_CUDA(launch_decompress(in, o, d_hdr, d_len, d_st, (uint32_t)cnt, nullptr, 0, w.ticket, c->num_sms, s));
@@ -337,7 +401,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
             PIPE_CUDA(cudaMemcpyAsync(&c->h()->pipe_summary[k & 3], w.summary, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, s));
             PIPE_CUDA(cudaEventRecord(ev_done[b], s));
         }
-        if (k >= lead) {
+        if (k >= lead && nchunks != SIZE_MAX) {
             const size_t kk = k - lead;
             const int b = (int)(kk % PIPE_DEPTH);
             PIPE_CUDA(cudaEventSynchronize(ev_done[b]));
@@ -346,6 +410,7 @@ static int decompress_frame_pipelined(b2lz4_ctx* c, const uint8_t* src, size_t n
             const size_t cnt = cfirst[kk + 1] - cfirst[kk];
             // every block of the chunk must be regular: no error, and exactly bs bytes unless it is the frame's last block
             if (sm.first_bad != 0xFFFFFFFFu || !sm.layout_ok || (!last && sm.total != (uint64_t)cnt * bs)) { unusual = true; break; }
+            if (cfirst[kk] * bs + sm.total > cap) { unusual = true; break; }
             if (cc) {
                 PIPE_CUDA(cudaStreamWaitEvent(c->side, ev_done[b], 0));
                 PIPE_CUDA(launch_xxh32_update(c->d_xxh(), c->stage_out[b].as<uint8_t>(), sm.total, c->side));
