@@ -361,9 +361,9 @@ static int encode_blocks_to_slots(b2lz4_ctx* c, const b2_ws_ref& w, const void* 
     } else {
         // Many more blocks than the GPU holds at once (28 / 14 per SM): expensive blocks first, so that the launch does
         // not end on a tail of expensive blocks drawn late.  (b2lz4_debug_tune("spare3", 1) switches it off; the
-        // host-pointer pipeline's chunks are below the threshold, so the context-wide scratch is never shared.)
+        // host-pointer pipeline's chunks are below the threshold.)
         const uint32_t slots_in_flight = (uint32_t)c->num_sms * (bs <= 65536 ? 28u : 14u);
-        if (nb >= 2 * slots_in_flight && bs >= 16384 && b2::tune().spare[3] == 0) {
+        if (nb >= 2 * slots_in_flight && bs >= 16384 && w.slots == &c->slots && b2::tune().spare[3] == 0) {   // (the context-wide scratch: workspace 0 only)
             B2_CUDA(c->order.ensure(order_scratch_bytes(nb)));
             B2_CUDA(launch_compress_fast_ordered(in, out, w.csize->as<uint32_t>(), w.status->as<int32_t>(), nb, (uint32_t)bs,
                                                  w.ticket, c->num_sms, c->order.p, s));

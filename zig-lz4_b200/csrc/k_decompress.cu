@@ -298,7 +298,7 @@ __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, ui
         uint8_t* ld = dst + o0;
         uint32_t rem = nl;
         for (uint32_t i0 = 0; i0 < mx; i0 += 4) {
-            uint32_t r[4];
+            uint32_t r[4] = {0u, 0u, 0u, 0u};   // (initialised: otherwise the predicated loads below make the compiler carry the old values through local memory)
 #pragma unroll
             for (int u = 0; u < 4; u++)
                 if ((uint32_t)u < rem) r[u] = __ldg(ls + u);
@@ -386,7 +386,7 @@ __device__ __forceinline__ bool expand_batch(const uint8_t* __restrict__ src, ui
                 uint8_t* pd = md;
                 uint32_t rem = nm;
                 for (uint32_t i0 = 0; i0 < mx; i0 += 8) {
-                    uint32_t r[8];
+                    uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int u = 0; u < 8; u++)
                         if ((uint32_t)u < rem) r[u] = ps[u];
@@ -783,10 +783,10 @@ cudaError_t launch_decompress(const BlockSet& in, const OutSet& out, const uint3
         order = order_scratch;
     }
     uint32_t want = (nblocks + K2_WARPS - 1) / K2_WARPS;
-    // CTAs of 4 warps per SM: 8 (64 registers, no spills) by default; b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
+    // CTAs of 4 warps per SM: 9 (56 registers, 36 warps) by default (8 / 9 / 10 measured 2.63 / 2.56 / 2.67 ms per GiB mixed); b2lz4_debug_tune("k2_occ") picks 10 or 12 for the
     // occupancy experiments of DESIGN.md, ("k2_variant", 1) the round-1 front end (10 per SM).
     const int occ_t = tune().k2_occ, variant = tune().k2_variant == 1 ? 1 : 2;
-    const int occ = (occ_t == 6 || occ_t == 7 || occ_t == 8 || occ_t == 9 || occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 8);   // the chunked decoder wants 64 registers
+    const int occ = (occ_t == 6 || occ_t == 7 || occ_t == 8 || occ_t == 9 || occ_t == 10 || occ_t == 12) ? occ_t : (variant == 1 ? 10 : 9);   // the chunked decoder wants 64 registers
     uint32_t maxg = (uint32_t)(num_sms * occ);
     uint32_t grid = want < maxg ? want : maxg;
 #define B2_K2_LAUNCH(N, V) k_decompress<N, V><<<grid, K2_THREADS, 0, stream>>>(in, out, hdr, out_len, status, nblocks, dict, \
