@@ -65,3 +65,32 @@ def test_host_pointer_pipeline_full_size(z, oracle, ctx):
     back = np.empty(n, dtype=np.uint8)
     m = ctx.decompress_frame(f, dst=back)
     assert m == n and (back == data).all()
+
+
+def test_ordered_launch_ragged_tail_and_single_class(z, oracle, ctx):
+    """The expensive-first launch order (estimate pass + explicit block sets + scatter of sizes and status words: frames of
+    at least 8288 blocks of 64 KiB): a frame whose last block is 321 bytes, block checksums on, and a single-class (text)
+    input where the estimate puts every block into one bucket — both equal the oracle's frames; the same frame with the
+    ordering switched off (b2lz4_debug_tune spare3) has the same bytes."""
+    import torch
+    from zig_lz4_b200 import datagen
+    n = 8300 * 65536 + 321
+    zp = z.lz4f.Preferences(blockSizeID=4, blockMode=1, blockChecksumFlag=1)
+    op = oracle.make_prefs(block_size_id=4, block_mode=1, block_checksum=1)
+    host, frame = _roundtrip(z, oracle, ctx, n, zp, op, 65536)
+    old = z.debug_tune("spare3", 1)
+    try:
+        src = host.to("cuda")
+        cap = z.lz4f.compressFrameBound(n, zp)
+        comp = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+        cs = ctx.compress_frame_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, 0)
+        assert cs == len(frame) and np.array_equal(comp[:cs].cpu().numpy(), frame)
+    finally:
+        z.debug_tune("spare3", old)
+    # one class only
+    text = torch.empty(n, dtype=torch.uint8).pin_memory()
+    datagen.fill_ptr(text.data_ptr(), n, mode=0, span=65536)
+    src = text.to("cuda")
+    cs = ctx.compress_frame_dev(src.data_ptr(), n, comp.data_ptr(), cap, zp, 0)
+    want = oracle.compress_frame(text.numpy(), op, threads=oracle.hardware_threads())
+    assert cs == len(want) and hashlib.sha1(comp[:cs].cpu().numpy().tobytes()).hexdigest() == hashlib.sha1(bytes(want)).hexdigest()
