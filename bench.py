@@ -667,6 +667,36 @@ def main():
                "d2h_bytes_per_step": world * (cs + n), "ms_per_step": round(dt / args.steps * 1e3, 3),
                "pcie_gbs_per_direction": round((n + cs) * args.steps / dt / 1e9, 2),
                "api": "b2lz4f_compress_frame_ctx + b2lz4f_decompress_frame_ctx (host pointers, pinned)"}
+        # the link itself, for the reader: raw pinned copies of 512 MiB, each direction alone and both at once
+        try:
+            pn = 512 << 20
+            d_a = torch.empty(pn, dtype=torch.uint8, device="cuda"); d_b = torch.empty(pn, dtype=torch.uint8, device="cuda")
+            s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def wall(fn):
+                best = 1e9
+                for _ in range(3):
+                    torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+                    best = min(best, time.perf_counter() - t0)
+                return best
+
+            def up():
+                with torch.cuda.stream(s_a):
+                    d_a.copy_(host[:pn], non_blocking=True)
+
+            def down():
+                with torch.cuda.stream(s_b):
+                    hback[:pn].copy_(d_b, non_blocking=True)
+
+            e2e["pcie_measured_gbs"] = {"h2d": round(pn / wall(up) / 1e9, 1), "d2h": round(pn / wall(down) / 1e9, 1),
+                                        "each_way_when_both_run": round(pn / wall(lambda: (up(), down())) / 1e9, 1),
+                                        "floor_ms_per_step": None}
+            both = e2e["pcie_measured_gbs"]["each_way_when_both_run"]
+            # two synchronous calls: the upload of N bytes bounds the first, the download of N bytes the second
+            e2e["pcie_measured_gbs"]["floor_ms_per_step"] = round(2 * n / both / 1e6, 1)
+            del d_a, d_b
+        except Exception as ex:      # never let the side measurement cost the line
+            e2e["pcie_measured_gbs"] = {"error": str(ex)[:80]}
         # what a caller with ordinary (pageable) slices gets: same calls, numpy-owned buffers
         psrc = np.array(hsrc, copy=True)
         pdst = np.empty(cap, dtype=np.uint8)

@@ -20,11 +20,14 @@
 //     exit tests are implied by the next distinct iteration's test.
 // Match extension (:401-413) compares 4 bytes per lane per round and finds the end with ballot/ffs.
 // Literal runs are copied with 16-byte aligned stores (b2::warp_copy).
+// That is the general path (any acceleration).  Acceleration 1 — compressDefault, every frame block — takes
+// compress_block_a1 below: windows of 32 consecutive positions that yield every sequence starting inside them (static
+// match chain + general step), one batched write per window, the input words of the window in a register ring.
 //
-// Memory: input is read straight from global memory through the read-only path (L1/L2 — a 64 KiB
-// block's window stays cache-resident while its warp works on it); the 4096-entry hash table lives in
-// shared memory: u16 entries when every block is <= 64 KiB (8 KiB/warp), u32 otherwise (16 KiB/warp).
-// Blocks are handed to warps through a global ticket so long and short blocks balance.
+// Memory: the 4096-entry hash table lives in shared memory: u16 entries when every block is <= 64 KiB (8 KiB/warp, 28
+// warps per SM), u32 otherwise (16 KiB/warp, 14 per SM).  Input: the window's words come from the register ring (a1 path)
+// or straight from global memory (general path); candidate bytes are read from global memory through L1/L2.  Blocks are
+// handed to warps through a global ticket; large launches take them expensive-first (launch_compress_fast_ordered).
 #include "b2_common.cuh"
 #ifndef B2_EMU
 #include "b2_kernels.h"

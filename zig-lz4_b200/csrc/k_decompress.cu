@@ -500,10 +500,12 @@ __device__ __noinline__ uint2 fast_v1_ool(const uint8_t* __restrict__ src, uint3
 // ---- chunked front end ----
 constexpr uint32_t CHUNK = 256;        // stream bytes whose token lengths are computed at once (8 per lane)
 constexpr uint32_t CHUNK_MARGIN = 32;  // staged bytes after the chunk: length-extension bytes of its last tokens
+constexpr bool WALK_IN_REGS = false;   // the walk's 32 positions in shared memory (true: lane k keeps step k in a register)
 constexpr uint32_t DELTA_SLOTS = 544;  // the walk may stand on any position < CHUNK + 2 + 269 + 2 + 2; slots >= CHUNK stay 0
 struct __align__(16) WarpStage {
     uint8_t bytes[CHUNK + CHUNK_MARGIN];
     uint16_t delta[DELTA_SLOTS];
+    uint16_t pos[40];                  // [32] = where the walk stands after its last step
 };
 
 // Token lengths of four positions at once, SPECULATIVELY: the bytes of `x` are candidate tokens, the bytes of `xs` the
@@ -569,12 +571,14 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
                 uint32_t d = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    if (lane == (uint32_t)(g8 * 8 + k)) myp2 = p2;
+                    if (WALK_IN_REGS) { if (lane == (uint32_t)(g8 * 8 + k)) myp2 = p2; }
+                    else ws->pos[g8 * 8 + k] = (uint16_t)p2;
                     d = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(ws->delta) + p2);
                     p2 += d;
                 }
                 if (g8 < 3 && d == 0) { steps = 8 * (g8 + 1); break; }   // the walk stands still: nothing more in this chunk
             }
+            if (!WALK_IN_REGS) { ws->pos[32] = (uint16_t)p2; myp2 = ws->pos[lane]; }   // (lanes >= steps: stale but in range)
             // ---------------- every lane decodes its own token from the staged bytes and checks the speculation ----------------
             const uint32_t mp = myp2 >> 1;                           // (lanes >= steps: position 0, in range, never live)
             const bool live = lane < steps && ws->delta[mp] != 0;    // halting (chunk end / exact-tier zone) is absorbing: a prefix of lanes
@@ -602,7 +606,7 @@ __device__ void decode_block_fast(const uint8_t* __restrict__ src, uint32_t n, u
             uint32_t k = (uint32_t)__popc(lm);
             const bool cut = bm != 0;                                // a token needs the exact tier: the batch ends before it
             if (cut) k = (uint32_t)__ffs(bm) - 1;
-            const uint32_t pk = __shfl_sync(FULL, myp2, k);          // (k == 32: where the walk stands after its last step)
+            const uint32_t pk = WALK_IN_REGS ? __shfl_sync(FULL, myp2, k) : (uint32_t)ws->pos[k];   // (k == 32: where the walk stands after its last step)
             const uint32_t ipn = (uint32_t)(cb + (int32_t)((k == 32 ? p2 : pk) >> 1));
             if (lane >= k) { myLL = 0; myML = 0; }
             // the next chunk's lines into L1 while this batch is expanded (its staging then costs an L1 hit, not an L2 round trip)
