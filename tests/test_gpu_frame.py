@@ -359,15 +359,31 @@ def test_pipelined_host_frames(z, oracle, small_pipeline_chunks, kw):
 
 
 def test_pipelined_host_decode_falls_back_exactly(z, oracle, small_pipeline_chunks):
-    """anything unusual inside a chunk (corruption, short output, short blocks) must give the oracle's result"""
+    """anything unusual inside a chunk (corruption, short output, short blocks) must give the oracle's result.  9 MiB = 144
+    blocks against 24-block chunks: long enough for the decode call to start before the header chain is walked to its end
+    (>= 4.4 chunks), so corruption found by the late part of the walk — after the first chunks are already in flight —
+    is covered too."""
     from zig_lz4_b200 import datagen
-    data = datagen.generate(6 << 20, mode=4, seed=5).tobytes()
+    data = datagen.generate(9 << 20, mode=4, seed=5).tobytes()
     zp, op = both_prefs(z, oracle, dict(block_mode=1, block_checksum=1, content_checksum=1), len(data))
     f = z.lz4f.compressFrame(data, zp)
     rng = np.random.default_rng(8)
     for _ in range(6):
         bad = bytearray(f)
         bad[int(rng.integers(7, len(bad)))] ^= int(rng.integers(1, 256))
+        _same_frame_result(z, oracle, bytes(bad), len(data))
+    # block headers damaged in the last third of the frame (found by the late part of the header walk): a size beyond
+    # the block size, a size running off the frame, a premature end mark
+    pos, offs = 7, []              # (header: magic, FLG, BD, HC — no contentSize in these preferences)
+    while True:
+        h = int.from_bytes(f[pos:pos + 4], "little")
+        if h == 0:
+            break
+        offs.append(pos)
+        pos += 4 + (h & 0x7FFFFFFF) + 4
+    for k, word in ((len(offs) - 3, 0x00020000), (len(offs) - 10, 0x7FFFFFF0), (len(offs) - 20, 0)):
+        bad = bytearray(f)
+        bad[offs[k]:offs[k] + 4] = word.to_bytes(4, "little")
         _same_frame_result(z, oracle, bytes(bad), len(data))
     for cap in (len(data) - 1, len(data) - 65536, 3 << 20, 65536 * 30 + 1):
         _same_frame_result(z, oracle, f, cap)
