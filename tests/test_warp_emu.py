@@ -1,4 +1,4 @@
-"""K1 / K2 device code executed on the host (tools/warp_emu: every lane a coroutine, every warp collective a rendezvous)
+"""K1 / K2 / K3 device code executed on the host (tools/warp_emu: every lane a coroutine, every warp collective a rendezvous)
 and compared with the oracle: the kernels' LOGIC — window walk, static match chain, batched emit, forward word ring,
 chunked / serial decode front ends, exact tier, error kinds — is checked here, where there is no GPU.  The GPU suite
 checks the compiled kernels; this one makes a logic regression visible in the CPU tier already.  Inputs and outputs sit
@@ -51,3 +51,16 @@ def test_k1_large_block_u32_tables_deferred_flush(emu_built):
 def test_k2_all_tiers_equal_oracle(emu_built, cls):
     """chunked front end, serial front end and exact tier: bytes, sizes and error kinds on intact, truncated and damaged streams"""
     run("emu_k2", cls, 1)
+
+
+@pytest.mark.parametrize("cls", [0, 1, 2, 4])
+def test_k3_hash_chain_equals_oracle(emu_built, cls):
+    """compressHC (src/lz4hc.zig:976-1064 with insertAndGetWiderMatch :538-681): levels 3 / 6 / 9, the hop-by-hop walk and
+    the jump-table walk, blocks compressed one after the other on ONE work area (epoch base, lazily built jump levels),
+    small inputs and limited-output exits — bytes and status codes equal the oracle's"""
+    run("emu_k3", cls, 2)
+
+
+def test_k3_64k_block_wraps_the_chain_window(emu_built):
+    """a full 64 KiB text block at level 9 (chains of up to 256 candidates, the pattern step, distances up to the window)"""
+    run("emu_k3", 0, 1, 65536)

@@ -25,7 +25,9 @@
 // epoch base (value = base + index; anything below the base reads as 0 = empty), so nothing is
 // re-zeroed between blocks, and the chain table never needs zeroing (only inserted slots are read).
 #include "b2_common.cuh"
+#ifndef B2_EMU   // (B2_EMU: host build of the device code for the one-warp emulator, tools/warp_emu)
 #include "b2_kernels.h"
+#endif
 
 namespace b2 {
 
@@ -53,6 +55,7 @@ struct HcWork {
     uint32_t base;                        // epoch base of the bucket values (persists across launches)
     uint32_t pad[15];
 };
+#ifndef B2_EMU
 static bool hc_jump() { return tune().k3_variant != 16; }     // 16 = the round-1 single-chain walk, for A/B runs
 
 // one work area per warp that a launch over `nblocks` blocks can have in flight — not per resident warp of the device:
@@ -61,6 +64,7 @@ size_t hc_work_bytes(int num_sms, uint32_t nblocks) {
     const size_t ctas = (nblocks + HC_WARPS - 1) / HC_WARPS, max_ctas = (size_t)num_sms * HC_CTAS_PER_SM;
     return (ctas < max_ctas ? ctas : max_ctas) * HC_WARPS * sizeof(HcWork);
 }
+#endif
 
 __device__ __forceinline__ uint32_t hashHC(uint32_t v) { return (v * HASH_MULTIPLIER) >> 17; }  // :129-131
 
@@ -402,6 +406,7 @@ __device__ void compress_block_hc(const uint8_t* __restrict__ src, uint32_t n, u
     olen = op;
 }
 
+#ifndef B2_EMU
 template <int CTAS, bool JUMP>
 __global__ void __launch_bounds__(HC_WARPS * 32, CTAS) k_compress_hc(BlockSet in, OutSet out, uint32_t* __restrict__ out_len,
                                                                int32_t* __restrict__ status, uint32_t nblocks, int nbs,
@@ -434,8 +439,8 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     const uint32_t few = (uint32_t)(num_sms * HC_CTAS_PER_SM_FEW);
     const int cap_ctas = tune().k3_variant;                 // experiment: 1..8 = at most this many CTAs (of 4 warps) per SM
     const bool jump = hc_jump() && nb_searches > 32;         // chains of at most 32 hops never earn the tables back
-    // a block switches to jump mode when its searches average more than this many chain hops (spare1 overrides: experiments)
-    const uint32_t jump_after = tune().spare[1] > 0 ? (uint32_t)tune().spare[1] : 24u;
+    // a block switches to jump mode when its searches average more than this many chain hops (spare5 overrides: experiments)
+    const uint32_t jump_after = tune().spare[5] > 0 ? (uint32_t)tune().spare[5] : 24u;
 #define B2_K3(C, J, G) k_compress_hc<C, J><<<(G), HC_WARPS * 32, 0, stream>>>(in, out, out_len, status, nblocks, nb_searches, work, ticket, jump_after)
     if (cap_ctas >= 1 && cap_ctas <= HC_CTAS_PER_SM_FEW) {
         const uint32_t g = (uint32_t)(num_sms * cap_ctas);
@@ -450,5 +455,6 @@ cudaError_t launch_compress_hc(const BlockSet& in, const OutSet& out, uint32_t* 
     count_launch();
     return cudaGetLastError();
 }
+#endif  // !B2_EMU
 
 }  // namespace b2

@@ -24,7 +24,10 @@
 //   the whole warp with 16-byte vector accesses.  Anything irregular — a stream end within 18 bytes,
 //   offset 0, a match reaching before dst (dictionary or corruption), output overflow — is not
 //   decided here: the fast tier stops at the start of that batch and the exact tier takes over.
-//   EXACT tier (decode_block): lock-step parse with the reference's checks in the reference's order;
+//   EXACT tier (decode_block): lock-step parse with the reference's checks in the reference's order — behind the fast
+//   tier for everything irregular, and the whole decoder of streams that shrink their block more than 6 x (runs and long
+//   matches: nearly every sequence is long, and this loop is compact — the kernel is ~9700 instructions, K2 notes in
+//   DESIGN.md);
 //   the byte work is spread over the lanes:
 //   * 255-run length extensions are scanned 32 bytes at a time with a ballot,
 //   * literals are copied with 16-byte aligned stores (b2::warp_copy, read-only source path),
