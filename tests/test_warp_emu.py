@@ -64,3 +64,18 @@ def test_k3_hash_chain_equals_oracle(emu_built, cls):
 def test_k3_64k_block_wraps_the_chain_window(emu_built):
     """a full 64 KiB text block at level 9 (chains of up to 256 candidates, the pattern step, distances up to the window)"""
     run("emu_k3", 0, 1, 65536)
+
+
+def test_reference_test_inputs_through_all_three_kernels(emu_built, tmp_path):
+    """the reference's own test inputs (tests/corpus.py: src/test_compat.zig:25-56, src/test.zig, test_lz4hc.zig, test_lz4f.zig
+    inputs, the F8 hazard input of SURVEY F8) through K1 (as one block and in 64 KiB blocks, accelerations 1 and 3, both
+    table widths), K2 (oracle streams of fast mode and HC 9, all three tiers) and K3 (levels 3 / 6 / 9, both walks)"""
+    from corpus import block_cases, compat_cases, f8_hazard_input
+    files = []
+    for i, (name, data) in enumerate(compat_cases() + block_cases() + [("f8", f8_hazard_input())]):
+        f = tmp_path / ("%03d_%s.bin" % (i, name))
+        f.write_bytes(data)
+        files.append("@" + str(f))
+    for binary in ("emu_k1", "emu_k2", "emu_k3"):
+        out = run(binary, *files)
+        assert "files:" in out

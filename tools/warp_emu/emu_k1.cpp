@@ -58,7 +58,34 @@ static void check(const uint8_t* src0, uint32_t n, uint32_t cap, uint32_t accel,
     }
 }
 
+static std::vector<uint8_t> read_file(const char* path) {
+    std::vector<uint8_t> d;
+    FILE* f = fopen(path, "rb");
+    if (!f) { perror(path); exit(2); }
+    uint8_t buf[65536];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) d.insert(d.end(), buf, buf + k);
+    fclose(f);
+    return d;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == '@') {
+        // file mode: every @path is one block (u16 tables up to 64 KiB, u32 above) at accelerations 1 and 3, and cut into
+        // 64 KiB blocks — the reference's own test inputs go through here (tests/test_warp_emu.py)
+        for (int a = 1; a < argc; a++) {
+            const std::vector<uint8_t> d = read_file(argv[a] + 1);
+            const uint32_t n = (uint32_t)d.size();
+            for (uint32_t accel : {1u, 3u}) check(d.data(), n, (uint32_t)b2o_compress_bound(n), accel, n > 65536, argv[a]);
+            if (n <= 65536) check(d.data(), n, (uint32_t)b2o_compress_bound(n), 1, true, argv[a]);
+            for (uint32_t o = 0; n > 65536 && o < n; o += 65536) {
+                const uint32_t len = n - o < 65536 ? n - o : 65536;
+                check(d.data() + o, len, (uint32_t)b2o_compress_bound(len), 1, false, argv[a]);
+            }
+        }
+        printf("files: %llu cases, %llu failed\n", (unsigned long long)g_checked, (unsigned long long)g_failed);
+        return g_failed ? 1 : 0;
+    }
     const int cls = argc > 1 ? atoi(argv[1]) : 4;
     const uint32_t blocks = argc > 2 ? (uint32_t)atoi(argv[2]) : 8;
     const uint32_t bs = argc > 3 ? (uint32_t)atoi(argv[3]) : 65536;

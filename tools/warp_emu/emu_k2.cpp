@@ -57,7 +57,34 @@ static void check(const uint8_t* comp, uint32_t clen, uint32_t cap, const char* 
     }
 }
 
+static std::vector<uint8_t> read_file(const char* path) {
+    std::vector<uint8_t> d;
+    FILE* f = fopen(path, "rb");
+    if (!f) { perror(path); exit(2); }
+    uint8_t buf[65536];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) d.insert(d.end(), buf, buf + k);
+    fclose(f);
+    return d;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == '@') {
+        // file mode: every @path is compressed by the oracle (fast mode and HC 9) and decoded by all three tiers
+        for (int a = 1; a < argc; a++) {
+            const std::vector<uint8_t> d = read_file(argv[a] + 1);
+            const uint32_t n = (uint32_t)d.size();
+            std::vector<uint8_t> comp(b2o_compress_bound(n) + 64);
+            size_t clen = 0;
+            b2o_compress_fast(d.data(), n, comp.data(), comp.size(), 1, &clen);
+            check(comp.data(), (uint32_t)clen, n, argv[a]);
+            if (n) check(comp.data(), (uint32_t)clen, n - 1, argv[a]);
+            b2o_compress_hc(d.data(), n, comp.data(), comp.size(), 9, &clen);
+            check(comp.data(), (uint32_t)clen, n + 3, argv[a]);
+        }
+        printf("files: %llu decodes checked, %llu failed\n", (unsigned long long)g_checked, (unsigned long long)g_failed);
+        return g_failed ? 1 : 0;
+    }
     const int cls = argc > 1 ? atoi(argv[1]) : 4;
     const uint32_t blocks = argc > 2 ? (uint32_t)atoi(argv[2]) : 4;
     const uint32_t bs = argc > 3 ? (uint32_t)atoi(argv[3]) : 65536;

@@ -39,7 +39,31 @@ static void check(b2::HcWork* work, bool jump, const uint8_t* src0, uint32_t n, 
     }
 }
 
+static std::vector<uint8_t> read_file(const char* path) {
+    std::vector<uint8_t> d;
+    FILE* f = fopen(path, "rb");
+    if (!f) { perror(path); exit(2); }
+    uint8_t buf[65536];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) d.insert(d.end(), buf, buf + k);
+    fclose(f);
+    return d;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == '@') {
+        // file mode: every @path as one block at levels 3, 6 and 9, both chain walks, on one work area
+        b2::HcWork* work = (b2::HcWork*)calloc(1, sizeof(b2::HcWork));
+        for (int a = 1; a < argc; a++) {
+            const std::vector<uint8_t> d = read_file(argv[a] + 1);
+            const uint32_t n = (uint32_t)d.size();
+            for (int level : {3, 6, 9})
+                for (bool jump : {false, true}) check(work, jump, d.data(), n, (uint32_t)b2o_compress_bound(n), level, argv[a]);
+        }
+        free(work);
+        printf("files: %llu blocks checked, %llu failed\n", (unsigned long long)g_checked, (unsigned long long)g_failed);
+        return g_failed ? 1 : 0;
+    }
     const int cls = argc > 1 ? atoi(argv[1]) : 0;
     const uint32_t blocks = argc > 2 ? (uint32_t)atoi(argv[2]) : 2;
     const uint32_t bs = argc > 3 ? (uint32_t)atoi(argv[3]) : 16384;
