@@ -31,7 +31,7 @@ def run(binary, *args):
 @pytest.mark.parametrize("cls", [0, 1, 2, 3, 4])
 def test_k1_fast_path_equals_oracle(emu_built, cls):
     """64 KiB blocks of every data class + edge sizes, capacities and unaligned starts (u16 and u32 tables), acceleration 1"""
-    out = run("emu_k1", cls, 2)
+    out = run("emu_k1", cls, 6)
     if cls in (0, 4):
         assert "batched 0)" not in out          # the static chain really ran
 
@@ -42,15 +42,17 @@ def test_k1_general_path_equals_oracle(emu_built, accel):
 
 
 def test_k1_large_block_u32_tables_deferred_flush(emu_built):
-    """256 KiB blocks: u32 tables, the variant that writes a window's batch under the next window's candidate reads"""
-    run("emu_k1", 0, 1, 262144)
-    run("emu_k1", 1, 1, 262144)
+    """large blocks: u32 tables, the variant that writes a window's batch under the next window's candidate reads — 1 MiB of
+    text, 1 MiB of binary records, and a 4 MiB block of all four classes (positions beyond 2^16 and 2^21)"""
+    run("emu_k1", 0, 1, 1048576)
+    run("emu_k1", 1, 1, 1048576)
+    run("emu_k1", 4, 1, 4194304)
 
 
 @pytest.mark.parametrize("cls", [0, 1, 2, 3, 4])
 def test_k2_all_tiers_equal_oracle(emu_built, cls):
     """chunked front end, serial front end and exact tier: bytes, sizes and error kinds on intact, truncated and damaged streams"""
-    run("emu_k2", cls, 1)
+    run("emu_k2", cls, 4)
 
 
 @pytest.mark.parametrize("cls", [0, 1, 2, 4])
@@ -61,9 +63,13 @@ def test_k3_hash_chain_equals_oracle(emu_built, cls):
     run("emu_k3", cls, 2)
 
 
-def test_k3_64k_block_wraps_the_chain_window(emu_built):
-    """a full 64 KiB text block at level 9 (chains of up to 256 candidates, the pattern step, distances up to the window)"""
+def test_k3_blocks_beyond_the_chain_window(emu_built):
+    """64 KiB blocks of text and binary records, and 256 KiB blocks (config 5's block size): positions beyond the 65 536-entry
+    chain table, distances clamped at the window, chains of up to 256 candidates, the pattern step"""
     run("emu_k3", 0, 1, 65536)
+    run("emu_k3", 1, 1, 65536)
+    run("emu_k3", 0, 1, 262144)
+    run("emu_k3", 2, 1, 262144)
 
 
 def test_reference_test_inputs_through_all_three_kernels(emu_built, tmp_path):
