@@ -4,7 +4,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 O=gpurun_out/$1; MODE=$2; K=${3:-k_compress_fast}
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"$K" -c 1 -o $O -f python tools/ncu_target.py --mib ${MIB:-1024} --mode $MODE > $O.ncu.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"$K" -c ${NCU_COUNT:-1} -o $O -f python tools/ncu_target.py --mib ${MIB:-1024} --mode $MODE > $O.ncu.log 2>&1
 ncu -i $O.ncu-rep --page raw --csv > $O.raw.csv 2>> $O.ncu.log
 ncu -i $O.ncu-rep --page source --csv --print-source cuda,sass > $O.source.csv 2>> $O.ncu.log
 ncu -i $O.ncu-rep --page source --csv --print-source sass > $O.sass.csv 2>> $O.ncu.log
